@@ -1,0 +1,152 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz from the REFERENCE.
+
+Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+For each case it (1) builds the reference's own module (NaDiT 3B/7B structure at
+reduced width, full-width VideoAutoencoderKLWrapper) through
+``oracle/ref_import.py``, (2) loads the deterministic synthetic checkpoint from
+``comfyui-seedvr2_videoupscaler_b200/weights.py``, (3) runs the reference forward on CPU fp32
+on seeded inputs, (4) asserts the restatements in ``oracle/dit_oracle.py`` /
+``oracle/vae_oracle.py`` reproduce it, and (5) stores the reference outputs.
+The fixtures pin the oracle; the GPU tests compare the CUDA path to the oracle.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import dit_oracle, vae_oracle  # noqa: E402
+from oracle.ref_import import import_reference_dit, import_reference_vae  # noqa: E402
+from svr2_import import load_package  # noqa: E402
+
+pkg = load_package()
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+DIT_CASES = {
+    # name: (variant, cfg overrides, (T, H, W) latent, txt_len)
+    "dit3b_tiny_t3": ("3b", dict(dim=256, heads=2, layers=4, mm_layers=2, txt_in_dim=64), (3, 40, 72), 58),
+    "dit3b_tiny_t5": ("3b", dict(dim=256, heads=2, layers=4, mm_layers=2, txt_in_dim=64), (5, 16, 24), 58),
+    "dit3b_tiny_img": ("3b", dict(dim=256, heads=2, layers=2, mm_layers=1, txt_in_dim=64), (1, 64, 64), 58),
+    "dit7b_tiny_t3": ("7b", dict(dim=384, heads=3, layers=3, mm_layers=3, txt_in_dim=64), (3, 40, 72), 58),
+}
+
+
+def dit_inputs(cfg, T, H, W, l, seed=42):
+    g = torch.Generator().manual_seed(seed)
+    vid = torch.randn(T * H * W, cfg["in_ch"], generator=g)
+    txt = torch.randn(l, cfg["txt_in_dim"], generator=g)
+    return vid, txt
+
+
+def build_ref_dit(cfg):
+    variant = cfg["variant"]
+    mod = import_reference_dit(variant)
+    L = cfg["layers"]
+    common = dict(vid_in_channels=cfg["in_ch"], vid_out_channels=cfg["out_ch"], vid_dim=cfg["dim"],
+                  txt_in_dim=cfg["txt_in_dim"], txt_dim=cfg["dim"], emb_dim=6 * cfg["dim"],
+                  heads=cfg["heads"], head_dim=cfg["head_dim"], expand_ratio=4, norm="fusedrms",
+                  norm_eps=1e-5, ada="single", qk_bias=False, qk_norm="fusedrms", patch_size=[1, 2, 2],
+                  num_layers=L, block_type=L * ["mmdit_sr"], window=L * [(4, 3, 3)],
+                  window_method=[("720pwin_by_size_bysize", "720pswin_by_size_bysize")[i % 2] for i in range(L)])
+    if variant == "3b":
+        net = mod.NaDiT(vid_out_norm="fusedrms", txt_in_norm="fusedln", mm_layers=cfg["mm_layers"],
+                        mlp_type="swiglu", msa_type=None, rope_type="mmrope3d", rope_dim=128, **common)
+    else:
+        net = mod.NaDiT(qk_rope=True, shared_mlp=False, shared_qkv=False, mlp_type="normal", **common)
+    return net.eval()
+
+
+def run_dit_case(name):
+    variant, over, (T, H, W), l = DIT_CASES[name]
+    cfg = dit_oracle.dit_config(variant, **over)
+    sd = pkg.weights.synth_dit_state_dict(cfg, seed=1234, dtype=torch.float16)
+    sd32 = {k: v.float() for k, v in sd.items()}
+    net = build_ref_dit(cfg)
+    missing = net.load_state_dict(sd32, strict=True)
+    vid, txt = dit_inputs(cfg, T, H, W, l)
+    with torch.no_grad():
+        kw = {} if variant == "3b" else {}
+        ref = net(vid=vid.clone(), txt=txt.clone(), vid_shape=torch.tensor([[T, H, W]]),
+                  txt_shape=torch.tensor([[l]]), timestep=torch.tensor([1000.0]), **kw).vid_sample
+    taps = {}
+    ora = dit_oracle.dit_forward(sd32, cfg, vid, txt, T, H, W, mode="fp32", taps=taps)
+    err = (ora - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"[{name}] ref |max|={scale:.3f} rms={ref.pow(2).mean().sqrt():.3f} oracle-vs-reference max|d|={err:.2e}")
+    assert err < 2e-4 * max(scale, 1.0), f"{name}: oracle deviates from reference ({err})"
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), out=ref.numpy().astype(np.float32),
+                        meta=np.array([T, H, W, l]),
+                        emb=taps["emb"].numpy(), block0=taps["block0"][::37].numpy())
+
+
+VAE_CASES = {
+    "vae_dec_t3": ("decode", (3, 4, 6)),     # latent T,h,w -> 9 frames 32x48
+    "vae_dec_img": ("decode", (1, 6, 4)),
+    "vae_enc_t9": ("encode", (9, 32, 48)),   # frames T,H,W -> latent 3x4x6
+    "vae_enc_img": ("encode", (1, 48, 32)),
+}
+
+
+def build_ref_vae():
+    mod = import_reference_vae()
+    vae = mod.VideoAutoencoderKLWrapper(
+        act_fn="silu", block_out_channels=[128, 256, 512, 512], down_block_types=["DownEncoderBlock3D"] * 4,
+        in_channels=3, latent_channels=16, layers_per_block=2, norm_num_groups=32, out_channels=3,
+        slicing_sample_min_size=4, temporal_scale_num=2, inflation_mode="pad",
+        up_block_types=["UpDecoderBlock3D"] * 4, spatial_downsample_factor=8, temporal_downsample_factor=4,
+        use_quant_conv=False, use_post_quant_conv=False, freeze_encoder=False)
+    return vae.eval()
+
+
+def run_vae_cases():
+    sd = pkg.weights.synth_vae_state_dict(seed=4321, dtype=torch.float16)
+    sd32 = {k: v.float() for k, v in sd.items()}
+    vae = build_ref_vae()
+    res = vae.load_state_dict(dict(sd32), strict=True)
+    print("vae load:", res)
+    # the reference pipeline enables temporal slicing (model_configuration.py:1247-1259)
+    vae.set_causal_slicing(split_size=4, memory_device="same")
+    for name, (kind, shp) in VAE_CASES.items():
+        g = torch.Generator().manual_seed(7)
+        if kind == "decode":
+            T, h, w = shp
+            z = torch.randn(1, 16, T, h, w, generator=g)
+            with torch.no_grad():
+                ref = vae.decode(z).sample
+                if ref.ndim == 4:
+                    ref = ref.unsqueeze(2)
+            ora = vae_oracle.vae_decode(sd32, z)
+        else:
+            T, H, W = shp
+            x = torch.rand(1, 3, T, H, W, generator=g) * 2 - 1
+            with torch.no_grad():
+                ref = vae.encode(x).latent
+                if ref.ndim == 4:
+                    ref = ref.unsqueeze(2)
+            ora = vae_oracle.vae_encode(sd32, x)
+        err = (ora - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        print(f"[{name}] out {tuple(ref.shape)} |max|={scale:.3f} oracle-vs-reference max|d|={err:.2e}")
+        assert err < 2e-4 * max(scale, 1.0), name
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), out=ref.numpy().astype(np.float32),
+                            meta=np.array(shp))
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    for name in DIT_CASES:
+        run_dit_case(name)
+    run_vae_cases()
+
+
+if __name__ == "__main__":
+    main()
