@@ -1,0 +1,296 @@
+// K4 — varlen (windowed) self-attention for head_dim = 128 on tcgen05.
+//
+// Drop-in for FlashAttentionVarlen.forward / pytorch_varlen_attention
+// (reference dit_3b/attention.py:27-64, 114-148): for every sequence i (one Swin
+// window + its 58 text tokens) and head h
+//      O_i = softmax(Q_i K_i^T / sqrt(128)) V_i        (non-causal, no mask)
+// on the packed (total, heads, 128) bf16 layout with int32 cu_seqlens.
+//
+// One CTA per (q-tile of 128 rows, sequence, head); 6 warps:
+//   warp 0    : TMA producer  (Q once, then a 2-stage ring of K/V tiles, 128B swizzle)
+//   warp 1    : MMA issuer    (S = Q K^T and O += P V, tcgen05.mma M=128,N=128,K=16, fp32 in TMEM;
+//                              V is consumed straight from its row-major tile as an MN-major B operand)
+//   warps 2-5 : softmax       (one query row per thread: tcgen05.ld the S row, online softmax in
+//                              registers with exp2, P -> bf16 -> swizzled smem as the A operand of P·V,
+//                              lazy rescale of O in TMEM, final 1/l and store)
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ptx.cuh"
+#include "svr2_internal.h"
+
+namespace svr2 {
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int ATT_BM = 128;      // q rows per CTA
+constexpr int ATT_BN = 128;      // kv rows per tile
+constexpr int ATT_D = 128;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_KV_STAGES = 2;
+constexpr int ATT_TILE_BYTES = 128 * 128 * 2;       // 32 KB: two [128 x 64] swizzled halves
+constexpr int ATT_HALF_BYTES = ATT_TILE_BYTES / 2;
+
+struct AttnSmem {
+  // offsets inside the 1024-aligned dynamic smem
+  static constexpr int kQ = 0;
+  static constexpr int kP = kQ + ATT_TILE_BYTES;
+  static constexpr int kKV = kP + ATT_TILE_BYTES;                       // stage s: K at +0, V at +32K
+  static constexpr int kBar = kKV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES;
+  static constexpr int kTotal = kBar + 256 + 1024;
+};
+
+struct AttnParams {
+  const int32_t* cu_seqlens;
+  const int32_t* out_row_map;
+  __nv_bfloat16* out;
+  int heads;
+  float scale_log2;  // softmax_scale * log2(e)
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  const int seq = blockIdx.y, head = blockIdx.z, qt = blockIdx.x;
+  const int s_begin = p.cu_seqlens[seq], s_end = p.cu_seqlens[seq + 1];
+  const int len = s_end - s_begin;
+  if (qt * ATT_BM >= len) return;
+  const int n_kv = (len + ATT_BN - 1) / ATT_BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::kBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;                  // [2]
+  uint64_t* kv_empty = bars + 3;                 // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_free = bars + 6;
+  uint64_t* p_ready = bars + 7;
+  uint64_t* pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ATT_KV_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_ready, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+
+  const int col0 = head * ATT_D;
+  const int q_row0 = s_begin + qt * ATT_BM;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_2d(smem + AttnSmem::kQ, &tmap_q, q_full, col0, q_row0);
+      tma_load_2d(smem + AttnSmem::kQ + ATT_HALF_BYTES, &tmap_q, q_full, col0 + 64, q_row0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* sk = smem + AttnSmem::kKV + stage * 2 * ATT_TILE_BYTES;
+        uint8_t* sv = sk + ATT_TILE_BYTES;
+        const int r0 = s_begin + j * ATT_BN;
+        mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+        tma_load_2d(sk, &tmap_k, &kv_full[stage], col0, r0);
+        tma_load_2d(sk + ATT_HALF_BYTES, &tmap_k, &kv_full[stage], col0 + 64, r0);
+        tma_load_2d(sv, &tmap_v, &kv_full[stage], col0, r0);
+        tma_load_2d(sv + ATT_HALF_BYTES, &tmap_v, &kv_full[stage], col0 + 64, r0);
+        if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // B (=V) is MN-major
+      const uint32_t q_addr = smem_u32(smem + AttnSmem::kQ);
+      const uint32_t p_addr = smem_u32(smem + AttnSmem::kP);
+      mbar_wait(q_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t k_addr = smem_u32(smem + AttnSmem::kKV + stage * 2 * ATT_TILE_BYTES);
+        const uint32_t v_addr = k_addr + ATT_TILE_BYTES;
+        mbar_wait(&kv_full[stage], phase);
+        if (j > 0) mbar_wait(s_free, (j - 1) & 1);     // softmax has finished reading S_{j-1}
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {                 // contraction over d = 128
+          const uint64_t da = umma_desc_kmajor_sw128(q_addr + (kk >> 2) * ATT_HALF_BYTES) + uint64_t((kk & 3) * 2);
+          const uint64_t db = umma_desc_kmajor_sw128(k_addr + (kk >> 2) * ATT_HALF_BYTES) + uint64_t((kk & 3) * 2);
+          umma_bf16(tmem_s, da, db, idesc_qk, kk != 0);
+        }
+        umma_commit(s_full);
+        mbar_wait(p_ready, j & 1);                       // P_j in smem, O rescaled
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {                 // contraction over kv = 128 (16 rows per MMA)
+          const uint64_t da = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * ATT_HALF_BYTES) + uint64_t((kk & 3) * 2);
+          const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, ATT_HALF_BYTES, 1024);
+          umma_bf16(tmem_o, da, db, idesc_pv, (j | kk) != 0);
+        }
+        umma_commit(&kv_empty[stage]);
+        umma_commit(pv_done);
+        if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ softmax warps (2..5)
+    const int quad = warp & 3;                 // TMEM lane quadrant accessible to this warp
+    const int row = quad * 32 + lane;          // query row within the tile
+    const uint32_t lane_off = uint32_t(quad * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* sp = smem + AttnSmem::kP;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t sv[128];
+      tmem_ld32(tmem_s + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      tmem_ld32(tmem_s + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      tmem_ld32(tmem_s + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[64]));
+      tmem_ld32(tmem_s + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&sv[96]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);                      // S may be overwritten by the next QK^T
+      const int kv_valid = len - j * ATT_BN;    // columns >= kv_valid are padding / next sequence
+      float mx = m_run;
+#pragma unroll
+      for (int c = 0; c < 128; ++c) {
+        float s = __uint_as_float(sv[c]);
+        s = (c < kv_valid) ? s : -INFINITY;
+        sv[c] = __float_as_uint(s);
+        mx = fmaxf(mx, s);
+      }
+      const float alpha = fast_exp2((m_run - mx) * p.scale_log2);   // 0 on the first tile (m_run = -inf)
+      const float mb = mx * p.scale_log2;
+      float lsum = 0.f;
+      // wait until P_{j-1}·V_{j-1} has completed before touching O or the P buffer
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (!__all_sync(0xffffffffu, alpha == 1.0f)) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld32(tmem_o + lane_off + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st32(tmem_o + lane_off + c0, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // P = exp2(s*scale - m*scale) -> bf16 -> swizzled K-major smem (row = this thread)
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) {          // 16-byte chunks of 8 kv columns
+        float pf[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          pf[e] = fast_exp2(__uint_as_float(sv[ch * 8 + e]) * p.scale_log2 - mb);
+          lsum += pf[e];
+        }
+        const int half = ch >> 3, cw = ch & 7;
+        uint8_t* dst = sp + half * ATT_HALF_BYTES + row * 128 + ((cw ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(pf[0], pf[1]), pack_bf16x2(pf[2], pf[3]),
+                                                    pack_bf16x2(pf[4], pf[5]), pack_bf16x2(pf[6], pf[7]));
+      }
+      l_run = l_run * alpha + lsum;
+      m_run = mx;
+      fence_proxy_async_smem();                  // make P visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    // ------------------------------ epilogue: O / l -> bf16 -> global
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int q_idx = qt * ATT_BM + row;
+    const bool valid = q_idx < len;
+    long long grow = (long long)(s_begin + q_idx);
+    if (valid && p.out_row_map) grow = p.out_row_map[grow];
+    __nv_bfloat16* orow = p.out + (grow * p.heads + head) * ATT_D;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t o[32];
+      tmem_ld32(tmem_o + lane_off + c0, o);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 pk = make_uint4(pack_bf16x2(__uint_as_float(o[e]) * inv_l, __uint_as_float(o[e + 1]) * inv_l),
+                                pack_bf16x2(__uint_as_float(o[e + 2]) * inv_l, __uint_as_float(o[e + 3]) * inv_l),
+                                pack_bf16x2(__uint_as_float(o[e + 4]) * inv_l, __uint_as_float(o[e + 5]) * inv_l),
+                                pack_bf16x2(__uint_as_float(o[e + 6]) * inv_l, __uint_as_float(o[e + 7]) * inv_l));
+          *reinterpret_cast<uint4*>(orow + c0 + e) = pk;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+}  // namespace svr2
+
+using namespace svr2;
+
+extern "C" int svr2_attn_varlen_bf16(const void* q, const void* k, const void* v, void* out,
+                                     const int32_t* cu_seqlens, int n_seq, int total, int heads, int max_seqlen,
+                                     const int32_t* out_row_map, void* stream) {
+  if (n_seq <= 0 || total <= 0) return SVR2_OK;
+  if (max_seqlen <= 0) return set_error(SVR2_ERR_ARG, "svr2_attn_varlen_bf16: max_seqlen must be > 0");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AttnSmem::kTotal);
+    if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
+    configured = true;
+  }
+  CUtensorMap tq, tk, tv;
+  uint64_t dims[2] = {(uint64_t)heads * ATT_D, (uint64_t)total};
+  uint64_t strides[1] = {(uint64_t)heads * ATT_D * 2};
+  uint32_t box[2] = {64, 128};
+  int rc = make_tmap_bf16(&tq, q, 2, dims, strides, box);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tk, k, 2, dims, strides, box);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tv, v, 2, dims, strides, box);
+  if (rc) return rc;
+  AttnParams p;
+  p.cu_seqlens = cu_seqlens;
+  p.out_row_map = out_row_map;
+  p.out = (__nv_bfloat16*)out;
+  p.heads = heads;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)ATT_D);
+  dim3 grid((max_seqlen + ATT_BM - 1) / ATT_BM, n_seq, heads);
+  attn_varlen_kernel<<<grid, ATT_THREADS, AttnSmem::kTotal, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  return check_launch("attn_varlen");
+}

@@ -1,0 +1,519 @@
+// HBM-bound kernels of the hot path: everything that is not a contraction.
+// All are one-read/one-write, 16-byte vectorised, fp32 math with bf16 rounding
+// at the reference's rounding points.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ptx.cuh"
+#include "svr2_internal.h"
+
+namespace svr2 {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int kWarps>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kWarps; ++i) t += red[i];
+  __syncthreads();
+  return t;
+}
+template <int kWarps>
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kWarps; ++i) t = fmaxf(t, red[i]);
+  __syncthreads();
+  return t;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------ RMSNorm + AdaSingle "in"
+// one block (256 threads) per row; dim % 8 == 0, dim <= 256*8*kVec
+template <int kVec>
+__global__ void __launch_bounds__(256) rmsnorm_ada_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          __nv_bfloat16* __restrict__ y, int dim, float eps,
+                                                          const float* __restrict__ weight,
+                                                          const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, int mode) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * dim);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * dim);
+  const int nvec = dim / 8;
+  float v[kVec][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < nvec) {
+      unpack8(xr[c], v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss += v[i][e] * v[i][e];
+    }
+  }
+  ss = block_sum<8>(ss, red);
+  const float rrms = 1.0f / sqrtf(ss / (float)dim + eps);
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < nvec) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ch = c * 8 + e;
+        // reference divides: x / sqrt(mean + eps)
+        float r = v[i][e] * rrms;
+        if (weight) r *= weight[ch];
+        if (mode == 0) {
+          o[e] = r * scale[ch] + shift[ch];
+        } else {
+          r = bf16_round(r);
+          r = bf16_round(r * scale[ch]);
+          o[e] = r + shift[ch];
+        }
+      }
+      yr[c] = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ q/k norm + RoPE + window gather
+// one block per output row (window-ordered); warp w handles heads w, w+nwarps, ...; lane = 4 dims.
+__global__ void __launch_bounds__(256) qk_norm_rope_window_kernel(
+    const __nv_bfloat16* __restrict__ qkv_vid, const __nv_bfloat16* __restrict__ qkv_txt,
+    const int32_t* __restrict__ row_src, const int32_t* __restrict__ row_rope, const float* __restrict__ cos_tab,
+    const float* __restrict__ sin_tab, int nfreq, const float* __restrict__ wq_vid, const float* __restrict__ wk_vid,
+    const float* __restrict__ wq_txt, const float* __restrict__ wk_txt, float eps, int heads,
+    __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, __nv_bfloat16* __restrict__ v) {
+  const long long r = blockIdx.x;
+  const int src = row_src[r];
+  const bool is_txt = src < 0;
+  const int inner = heads * 128;
+  const __nv_bfloat16* base = is_txt ? qkv_txt + (long long)(-src - 1) * 3 * inner : qkv_vid + (long long)src * 3 * inner;
+  const float* wq = is_txt ? wq_txt : wq_vid;
+  const float* wk = is_txt ? wk_txt : wk_vid;
+  const int ri[3] = {row_rope[r * 3 + 0], row_rope[r * 3 + 1], row_rope[r * 3 + 2]};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int d0 = lane * 4;
+  const int rot = 6 * nfreq;  // rotated dims
+  // per-lane cos/sin for the two pairs (d0,d0+1), (d0+2,d0+3)
+  float cs[2], sn[2];
+#pragma unroll
+  for (int pi = 0; pi < 2; ++pi) {
+    const int d = d0 + 2 * pi;
+    cs[pi] = 1.f;
+    sn[pi] = 0.f;
+    if (d < rot) {
+      const int axis = d / (2 * nfreq), j = (d % (2 * nfreq)) >> 1;
+      const int tr = ri[axis];
+      if (tr >= 0) {
+        cs[pi] = cos_tab[tr * nfreq + j];
+        sn[pi] = sin_tab[tr * nfreq + j];
+      }
+    }
+  }
+  const float4 wq4 = *reinterpret_cast<const float4*>(wq + d0);
+  const float4 wk4 = *reinterpret_cast<const float4*>(wk + d0);
+  for (int h = warp; h < heads; h += nwarps) {
+    const long long o_off = (r * heads + h) * 128 + d0;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(base + which * inner + h * 128 + d0);
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      float2 a = __bfloat1622float2(hh[0]), b = __bfloat1622float2(hh[1]);
+      float ss = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+      ss = warp_sum(ss);
+      const float rr = 1.0f / sqrtf(ss * (1.0f / 128.0f) + eps);
+      const float4 w4 = which == 0 ? wq4 : wk4;
+      float x0 = a.x * rr * w4.x, x1 = a.y * rr * w4.y, x2 = b.x * rr * w4.z, x3 = b.y * rr * w4.w;
+      // interleaved-pair rotation: (x0,x1) -> (x0 c - x1 s, x1 c + x0 s)
+      const float y0 = x0 * cs[0] - x1 * sn[0], y1 = x1 * cs[0] + x0 * sn[0];
+      const float y2 = x2 * cs[1] - x3 * sn[1], y3 = x3 * cs[1] + x2 * sn[1];
+      uint2 outv = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+      *reinterpret_cast<uint2*>((which == 0 ? q : k) + o_off) = outv;
+    }
+    *reinterpret_cast<uint2*>(v + o_off) = *reinterpret_cast<const uint2*>(base + 2 * inner + h * 128 + d0);
+  }
+}
+
+// ------------------------------------------------------------------ text mean over windows
+__global__ void txt_window_mean_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                       int n_win, int l, int dim) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over l*dim/8 vectors
+  const long long nvec = (long long)l * dim / 8;
+  if (idx >= nvec) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int w = 0; w < n_win; ++w) {
+    float f[8];
+    unpack8(reinterpret_cast<const uint4*>(in + (long long)w * l * dim)[idx], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+  }
+  const float inv = 1.0f / (float)n_win;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] *= inv;
+  reinterpret_cast<uint4*>(out)[idx] = pack8(acc);
+}
+
+// ------------------------------------------------------------------ patchify / unpatchify (1,2,2)
+__global__ void patchify_kernel(const __nv_bfloat16* __restrict__ vid, __nv_bfloat16* __restrict__ out, int T, int H,
+                                int W, int C, int ld_out) {
+  const int Hp = H / 2, Wp = W / 2;
+  const long long l = blockIdx.x;  // token
+  const int wp = l % Wp, hp = (l / Wp) % Hp, t = l / ((long long)Wp * Hp);
+  for (int i = threadIdx.x; i < ld_out; i += blockDim.x) {
+    float val = 0.f;
+    if (i < 4 * C) {
+      const int c = i % C, dw = (i / C) & 1, dh = i / (2 * C);
+      val = __bfloat162float(vid[(((long long)t * H + 2 * hp + dh) * W + 2 * wp + dw) * C + c]);
+    }
+    out[l * ld_out + i] = __float2bfloat16_rn(val);
+  }
+}
+__global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, __nv_bfloat16* __restrict__ out,
+                                  int T, int H, int W, int C) {
+  const int Hp = H / 2, Wp = W / 2;
+  const long long l = blockIdx.x;
+  const int wp = l % Wp, hp = (l / Wp) % Hp, t = l / ((long long)Wp * Hp);
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+    const int c = i % C, dw = (i / C) & 1, dh = i / (2 * C);
+    out[(((long long)t * H + 2 * hp + dh) * W + 2 * wp + dw) * C + c] = in[l * ld_in + i];
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm(32) per frame
+// stats: block handles a slab of pixels of one frame, all channels; thread owns 8 consecutive channels.
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, int hw, int C,
+                                                              int pix_per_block, double* __restrict__ stats) {
+  extern __shared__ float sm[];  // [2][32]
+  const int f = blockIdx.y;
+  const int cvec = C / 8;               // vectors per pixel
+  const int cpg = C / 32;               // channels per group (4, 8, 16)
+  if (threadIdx.x < 64) sm[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  const long long p1 = min((long long)hw, p0 + pix_per_block);
+  const __nv_bfloat16* xf = x + (long long)f * hw * C;
+  // thread -> fixed channel vector (tid % cvec), strided over pixels
+  const int cv = threadIdx.x % cvec, pl = threadIdx.x / cvec, pstride = blockDim.x / cvec;
+  float s[2] = {0.f, 0.f}, ss[2] = {0.f, 0.f};  // cpg==4: a vector spans 2 groups
+  for (long long p = p0 + pl; p < p1; p += pstride) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(xf + p * C + cv * 8), v);
+    if (cpg == 4) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s[0] += v[e]; ss[0] += v[e] * v[e]; s[1] += v[4 + e]; ss[1] += v[4 + e] * v[4 + e]; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s[0] += v[e]; ss[0] += v[e] * v[e]; }
+    }
+  }
+  if (cpg == 4) {
+    atomicAdd(&sm[cv * 2], s[0]); atomicAdd(&sm[32 + cv * 2], ss[0]);
+    atomicAdd(&sm[cv * 2 + 1], s[1]); atomicAdd(&sm[32 + cv * 2 + 1], ss[1]);
+  } else {
+    const int g = (cv * 8) / cpg;
+    atomicAdd(&sm[g], s[0]); atomicAdd(&sm[32 + g], ss[0]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x & 31, which = threadIdx.x >> 5;
+    atomicAdd(&stats[((long long)f * 32 + g) * 2 + which], (double)sm[threadIdx.x]);
+  }
+}
+
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              __nv_bfloat16* __restrict__ y, int hw, int C,
+                                                              const __nv_bfloat16* __restrict__ gamma,
+                                                              const __nv_bfloat16* __restrict__ beta, float eps,
+                                                              int silu, int out_t_pad, int out_dup_head,
+                                                              const double* __restrict__ stats) {
+  const int f = blockIdx.y;
+  const int cvec = C / 8, cpg = C / 32;
+  const long long nvec = (long long)hw * cvec;
+  const double n = (double)hw * cpg;
+  const __nv_bfloat16* xf = x + (long long)f * hw * C;
+  __nv_bfloat16* yf = y + (long long)(f + out_t_pad) * hw * C;
+  // 256 % cvec == 0 and the grid stride is a multiple of 256, so a thread always owns the same 8 channels
+  const int cv = threadIdx.x % cvec;
+  float ca[8], cb[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ch = cv * 8 + e, g = ch / cpg;
+    const double mean_d = stats[((long long)f * 32 + g) * 2] / n;
+    const double var_d = stats[((long long)f * 32 + g) * 2 + 1] / n - mean_d * mean_d;
+    const float rstd = rsqrtf(fmaxf((float)var_d, 0.f) + eps);
+    ca[e] = rstd * __bfloat162float(gamma[ch]);
+    cb[e] = __bfloat162float(beta[ch]) - (float)mean_d * ca[e];
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v[8], o[8];
+    unpack8(reinterpret_cast<const uint4*>(xf)[i], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = bf16_round(v[e] * ca[e] + cb[e]);   // F.group_norm output is bf16
+      o[e] = silu ? silu_f(t) : t;
+    }
+    const uint4 pk = pack8(o);
+    reinterpret_cast<uint4*>(yf)[i] = pk;
+    if (out_dup_head && f == 0) {
+      reinterpret_cast<uint4*>(yf - (long long)hw * C)[i] = pk;
+      reinterpret_cast<uint4*>(yf - 2LL * hw * C)[i] = pk;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ softmax rows fp32 -> bf16
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, long long lds,
+                                                           __nv_bfloat16* __restrict__ p, long long ldp, int cols) {
+  __shared__ float red[8];
+  const float* sr = s + (long long)blockIdx.x * lds;
+  __nv_bfloat16* pr = p + (long long)blockIdx.x * ldp;
+  float m = -INFINITY;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(sr + c);
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  m = block_max<8>(m, red);
+  float sum = 0.f;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(sr + c);
+    sum += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+  }
+  sum = block_sum<8>(sum, red);
+  const float inv = 1.0f / sum;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(sr + c);
+    uint2 o = make_uint2(pack_bf16x2(__expf(v.x - m) * inv, __expf(v.y - m) * inv),
+                         pack_bf16x2(__expf(v.z - m) * inv, __expf(v.w - m) * inv));
+    *reinterpret_cast<uint2*>(pr + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------ transpose bf16 [rows, cols] -> [cols, rows]
+__global__ void transpose_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out,
+                                 long long ld_out, int rows, int cols) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * ld_in + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(long long)c * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------ layout glue
+template <typename TIn>
+__device__ __forceinline__ float ld_as_float(const TIn* p, long long i);
+template <> __device__ __forceinline__ float ld_as_float<float>(const float* p, long long i) { return p[i]; }
+template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
+template <> __device__ __forceinline__ float ld_as_float<__half>(const __half* p, long long i) { return __half2float(p[i]); }
+
+// in: [C,T,H,W] -> out: [out_t_pad + T, H, W, C_pad] (channels >= C zero), frame 0 duplicated into the halo
+template <typename TIn>
+__global__ void ncdhw_to_ndhwc_kernel(const TIn* __restrict__ in, int C, int T, int H, int W,
+                                      __nv_bfloat16* __restrict__ out, int C_pad, int out_t_pad, float div) {
+  const long long hw = (long long)H * W;
+  const long long total = (long long)T * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / hw, pix = i % hw;
+    for (int c = 0; c < C_pad; ++c) {
+      const float v = c < C ? bf16_round(ld_as_float<TIn>(in, ((long long)c * T + t) * hw + pix)) / div : 0.f;
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      out[((t + out_t_pad) * hw + pix) * C_pad + c] = b;
+      if (t == 0)
+        for (int d = 0; d < out_t_pad; ++d) out[((long long)d * hw + pix) * C_pad + c] = b;
+    }
+  }
+}
+// in: [T,H,W,ld_in] -> out [C,T,H,W] (first C channels)
+template <typename TOut>
+__global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int C, int T, int H, int W,
+                                      TOut* __restrict__ out) {
+  const long long hw = (long long)H * W, total = (long long)T * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / hw, pix = i % hw;
+    for (int c = 0; c < C; ++c) {
+      const float v = __bfloat162float(in[i * ld_in + c]);
+      if constexpr (sizeof(TOut) == 4) out[((long long)c * T + t) * hw + pix] = v;
+      else out[((long long)c * T + t) * hw + pix] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// 3x3x3 im2col, zero spatial padding, causal halo = 2 real frames in front of x.
+// x [2+T, H, W, ld_in] (C real channels) -> out [T*H*W, ld_out], column ((kt*3+kh)*3+kw)*C + c
+__global__ void im2col3_kernel(const __nv_bfloat16* __restrict__ x, int T, int H, int W, int C, int ld_in,
+                               __nv_bfloat16* __restrict__ out, int ld_out) {
+  const long long total = (long long)T * H * W;
+  const long long row = blockIdx.x;
+  if (row >= total) return;
+  const int w = row % W, h = (row / W) % H, t = row / ((long long)W * H);
+  for (int i = threadIdx.x; i < ld_out; i += blockDim.x) {
+    __nv_bfloat16 val = __float2bfloat16(0.f);
+    if (i < 27 * C) {
+      const int c = i % C, tap = i / C, kw = tap % 3, kh = (tap / 3) % 3, kt = tap / 9;
+      const int hh = h + kh - 1, ww = w + kw - 1, tt = t + kt;  // halo offset already included
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = x[(((long long)tt * H + hh) * W + ww) * ld_in + c];
+    }
+    out[row * ld_out + i] = val;
+  }
+}
+
+}  // namespace svr2
+
+using namespace svr2;
+
+extern "C" int svr2_rmsnorm_ada_bf16(const void* x, void* y, int rows, int dim, float eps, const float* weight,
+                                     const float* scale, const float* shift, int mode, void* stream) {
+  if (dim % 8 || dim > 256 * 8 * 2) return set_error(SVR2_ERR_ARG, "svr2_rmsnorm_ada_bf16: dim % 8 != 0 or dim > 4096");
+  if (rows <= 0) return SVR2_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dim <= 2048)
+    rmsnorm_ada_kernel<1><<<rows, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, dim, eps, weight, scale, shift, mode);
+  else
+    rmsnorm_ada_kernel<2><<<rows, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, dim, eps, weight, scale, shift, mode);
+  return check_launch("rmsnorm_ada");
+}
+
+extern "C" int svr2_qk_norm_rope_window_bf16(const void* qkv_vid, const void* qkv_txt, const int32_t* row_src,
+                                             const int32_t* row_rope, const float* cos_tab, const float* sin_tab,
+                                             int nfreq, const float* wq_vid, const float* wk_vid, const float* wq_txt,
+                                             const float* wk_txt, float eps, int total, int heads, void* q, void* k,
+                                             void* v, void* stream) {
+  if (total <= 0) return SVR2_OK;
+  if (6 * nfreq > 128) return set_error(SVR2_ERR_ARG, "rope: 6*nfreq > head_dim");
+  const int threads = heads >= 8 ? 256 : 32 * heads;
+  qk_norm_rope_window_kernel<<<total, threads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)qkv_vid, (const __nv_bfloat16*)qkv_txt, row_src, row_rope, cos_tab, sin_tab, nfreq, wq_vid,
+      wk_vid, wq_txt, wk_txt, eps, heads, (__nv_bfloat16*)q, (__nv_bfloat16*)k, (__nv_bfloat16*)v);
+  return check_launch("qk_norm_rope_window");
+}
+
+extern "C" int svr2_txt_window_mean_bf16(const void* in, void* out, int n_win, int l, int dim, void* stream) {
+  if (dim % 8) return set_error(SVR2_ERR_ARG, "txt_window_mean: dim % 8");
+  const long long nvec = (long long)l * dim / 8;
+  txt_window_mean_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, n_win, l, dim);
+  return check_launch("txt_window_mean");
+}
+
+extern "C" int svr2_patchify_bf16(const void* vid, void* out, int T, int H, int W, int C, int ld_out, void* stream) {
+  if ((H | W) & 1) return set_error(SVR2_ERR_ARG, "patchify: H, W must be even");
+  const long long L = (long long)T * (H / 2) * (W / 2);
+  patchify_kernel<<<(unsigned)L, 64, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)vid, (__nv_bfloat16*)out, T, H, W, C, ld_out);
+  return check_launch("patchify");
+}
+extern "C" int svr2_unpatchify_bf16(const void* in, int ld_in, void* out, int T, int H, int W, int C, void* stream) {
+  const long long L = (long long)T * (H / 2) * (W / 2);
+  unpatchify_kernel<<<(unsigned)L, 64, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, ld_in, (__nv_bfloat16*)out, T, H, W, C);
+  return check_launch("unpatchify");
+}
+
+extern "C" int svr2_groupnorm_bf16(const void* x, void* y, int frames, int hw, int C, const void* gamma,
+                                   const void* beta, float eps, int silu, int out_t_pad, int out_dup_head,
+                                   double* stats, void* stream) {
+  if (C % 32 || (C / 32 != 4 && C / 32 != 8 && C / 32 != 16) || 256 % (C / 8))
+    return set_error(SVR2_ERR_ARG, "groupnorm: C must be 128, 256 or 512");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 64 * frames, s);
+  if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
+  // ~4 waves of blocks per frame set
+  int blocks_x = (int)((hw + 2047) / 2048);
+  if (blocks_x < 1) blocks_x = 1;
+  const int ppb = (hw + blocks_x - 1) / blocks_x;
+  groupnorm_stats_kernel<<<dim3(blocks_x, frames), 256, 64 * sizeof(float), s>>>((const __nv_bfloat16*)x, hw, C, ppb, stats);
+  int rc = check_launch("groupnorm_stats");
+  if (rc) return rc;
+  const long long nvec = (long long)hw * C / 8;
+  int bx = (int)((nvec + 256 * 4 - 1) / (256 * 4));
+  if (bx < 1) bx = 1;
+  groupnorm_apply_kernel<<<dim3(bx, frames), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, C,
+                                                          (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps,
+                                                          silu, out_t_pad, out_dup_head, stats);
+  return check_launch("groupnorm_apply");
+}
+
+extern "C" int svr2_softmax_rows_bf16(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols,
+                                      void* stream) {
+  if (cols % 4 || lds % 4 || ldp % 4) return set_error(SVR2_ERR_ARG, "softmax_rows: cols/lds/ldp % 4");
+  if (rows <= 0) return SVR2_OK;
+  softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(s, lds, (__nv_bfloat16*)p, ldp, cols);
+  return check_launch("softmax_rows");
+}
+
+extern "C" int svr2_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols,
+                                   void* stream) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, ld_in, (__nv_bfloat16*)out, ld_out, rows, cols);
+  return check_launch("transpose");
+}
+
+extern "C" int svr2_ncdhw_to_ndhwc_bf16(const void* in, int in_dtype, int C, int T, int H, int W, void* out, int C_pad,
+                                        int out_t_pad, float div, void* stream) {
+  const long long total = (long long)T * H * W;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (in_dtype == 0) ncdhw_to_ndhwc_kernel<float><<<blocks, 256, 0, s>>>((const float*)in, C, T, H, W, (__nv_bfloat16*)out, C_pad, out_t_pad, div);
+  else if (in_dtype == 1) ncdhw_to_ndhwc_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, C, T, H, W, (__nv_bfloat16*)out, C_pad, out_t_pad, div);
+  else if (in_dtype == 2) ncdhw_to_ndhwc_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)in, C, T, H, W, (__nv_bfloat16*)out, C_pad, out_t_pad, div);
+  else return set_error(SVR2_ERR_ARG, "ncdhw_to_ndhwc: dtype must be 0 (f32), 1 (bf16) or 2 (f16)");
+  return check_launch("ncdhw_to_ndhwc");
+}
+extern "C" int svr2_ndhwc_to_ncdhw(const void* in, int ld_in, int C, int T, int H, int W, void* out, int out_dtype,
+                                   void* stream) {
+  const long long total = (long long)T * H * W;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (out_dtype == 0) ndhwc_to_ncdhw_kernel<float><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, ld_in, C, T, H, W, (float*)out);
+  else if (out_dtype == 1) ndhwc_to_ncdhw_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, ld_in, C, T, H, W, (__nv_bfloat16*)out);
+  else return set_error(SVR2_ERR_ARG, "ndhwc_to_ncdhw: dtype must be 0 (f32) or 1 (bf16)");
+  return check_launch("ndhwc_to_ncdhw");
+}
+extern "C" int svr2_im2col3_bf16(const void* x, int T, int H, int W, int C, int ld_in, void* out, int ld_out,
+                                 void* stream) {
+  const long long total = (long long)T * H * W;
+  im2col3_kernel<<<(unsigned)total, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, T, H, W, C, ld_in, (__nv_bfloat16*)out, ld_out);
+  return check_launch("im2col3");
+}

@@ -1,0 +1,605 @@
+// K1/K6 — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] = A[M,K] · B[N,K]^T   (bf16 x bf16 -> fp32 in TMEM -> fused epilogue)
+//
+// One kernel body serves the DiT Linear layers (A = activation rows, 2-D TMA)
+// and the VAE causal Conv3d as an implicit GEMM (A = shifted NDHWC boxes fetched
+// by 4-D/5-D TMA with out-of-bounds zero fill = spatial zero padding; the causal
+// temporal halo is two real frames stored in front of every activation tensor).
+//
+// Roles (256 threads, 1 CTA / SM, grid = #SMs, static tile schedule):
+//   warp 0 : TMA producer   (kStages-deep smem ring, 128B-swizzled K-major tiles)
+//   warp 1 : MMA issuer     (one elected lane, tcgen05.mma cta_group::1, M=128,N=BLOCK_N,K=16)
+//   warp 2 : TMEM allocator (2 accumulator stages so the epilogue overlaps the next tile)
+//   warps 4-7 : epilogue    (tcgen05.ld 32x32b -> registers -> fused math -> 16-byte global stores)
+//
+// Reference semantics replaced: nn.Linear (dit_3b/mmattn.py:56-59,173,269; mlp.py:56-61;
+// patch_v1.py:37,62), InflatedCausalConv3d (causal_inflation_lib.py:213-305), Upsample3D's
+// 1x1x1 conv + pixel shuffle (attn_video_vae.py:135-143), with the elementwise ops around
+// them (bias, AdaSingle gate, residual add, SwiGLU, GELU) fused into the epilogue and
+// rounded to bf16 at the same points as the reference's bf16 path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ptx.cuh"
+#include "svr2_internal.h"
+
+namespace svr2 {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 256;
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  // ---- A addressing (conv) ----
+  int a_mode;            // 0 linear (2-D [M,K]); 1 conv stride-1 (4-D C,W,H,T); 2 conv spatial stride-2 (5-D pair view)
+  int tiles_w, tiles_h;  // M tiles per output frame
+  int bw, bh;            // output pixels per tile: bw*bh == 128
+  int taps_t, taps_h, taps_w;
+  int cin_blocks;        // Cin / 64
+  int cin;               // Cin (pair view channel offset)
+  int pad_h, pad_w;      // subtracted from the tap offset (1 for padding=1)
+  int stride_t;          // temporal stride of the conv (1 or 2)
+  int H_out, W_out, T_out;
+  // ---- epilogue ----
+  int epi;               // EPI_* flags
+  int ldc;               // elements between consecutive output rows/pixels
+  long long out_frame_stride;  // conv/shuffle: elements per output frame
+  int out_t_pad;         // leading halo frames in the output tensor (0 or 2)
+  int out_dup_head;      // also write frame 0 into the halo frames
+  int shuf_c, shuf_z;    // pixel shuffle: channels per output voxel, temporal factor
+  int shuf_H, shuf_W;    // input H,W of the shuffle GEMM (rows are (f,h,w))
+  int shuf_drop;         // drop the duplicated first output frame (first chunk)
+  float out_scale;       // fp32 output scale
+  const __nv_bfloat16* bias;      // [N] or null
+  const float* gate;              // [N] or null
+  const __nv_bfloat16* residual;  // same layout as out, or null
+  void* out;
+};
+
+enum : int {
+  EPI_BIAS = 1,
+  EPI_GATE = 2,       // t = bf16(t * gate[n])
+  EPI_RESIDUAL = 4,   // out = bf16(t + res)
+  EPI_SWIGLU = 8,     // out[:, j] = bf16(bf16(silu(bf16 acc[j])) * bf16 acc[j + BLOCK_N/2]) per tile
+  EPI_GELU = 16,      // t = gelu_tanh(t)
+  EPI_F32 = 32,       // fp32 output = acc * out_scale (no rounding)
+  EPI_SHUFFLE = 64,   // Upsample3D pixel shuffle store
+  EPI_SILU = 128,     // t = bf16(silu(t))
+};
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+  using L = SmemLayout<BLOCK_N>;
+  constexpr int kStages = L::kStages;
+  constexpr int ACC_STRIDE = BLOCK_N < 32 ? 32 : BLOCK_N;   // TMEM columns per accumulator stage
+  constexpr uint32_t kTmemCols = (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128) ? 128
+                                 : (2 * ACC_STRIDE <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0) {
+    // ========================= TMA producer =========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+        int t_o = 0, h0 = 0, w0 = 0;
+        if (p.a_mode != 0) {
+          const int per_frame = p.tiles_w * p.tiles_h;
+          t_o = m_blk / per_frame;
+          const int r = m_blk % per_frame;
+          h0 = (r / p.tiles_w) * p.bh;
+          w0 = (r % p.tiles_w) * p.bw;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          if (p.a_mode == 0) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+            const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
+            const int kw_ = tap % p.taps_w, kh_ = (tap / p.taps_w) % p.taps_h, kt_ = tap / (p.taps_w * p.taps_h);
+            const int t_in = t_o * p.stride_t + kt_;
+            if (p.a_mode == 1) {
+              tma_load_4d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, w0 + kw_ - p.pad_w, h0 + kh_ - p.pad_h, t_in);
+            } else {
+              // pair view (2C, W/2, 2, H/2, T): input pixel 2*o + k -> pair o + k/2, phase k%2
+              tma_load_5d(sa, &tmap_a, &full_bar[stage], (kw_ & 1) * p.cin + cb * BLOCK_K, w0 + (kw_ >> 1),
+                          kh_ & 1, h0 + (kh_ >> 1), t_in);
+            }
+          }
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ========================= MMA issuer =========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
+          const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in the >>4 address field
+            umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);      // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ========================= epilogue =========================
+    const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;        // tile row owned by this thread
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr int N_OUT = ACC_STRIDE;      // accumulator columns read per tile
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      // ---- where does this row go? ----
+      bool valid;
+      long long off0 = 0, off_dup1 = -1, off_dup2 = -1;
+      if (p.epi & EPI_SHUFFLE) {
+        const int m = m_blk * BLOCK_M + row;
+        valid = m < p.M;
+        const int hw = p.shuf_H * p.shuf_W;
+        const int f = m / hw, rr = m % hw, h = rr / p.shuf_W, w = rr % p.shuf_W;
+        // channel n = ((x*2 + y)*Z + z)*C + c ; a BLOCK_N tile never straddles a (x,y,z) group
+        const int grp = (n_blk * BLOCK_N) / p.shuf_c;
+        const int z = grp % p.shuf_z, y = (grp / p.shuf_z) & 1, x = grp / (p.shuf_z * 2);
+        int t_out = f * p.shuf_z + z;
+        if (p.shuf_drop) {
+          // remove_head (causal_inflation_lib.py:412-419): keep (f=0,z=0), drop (f=0,z=1)
+          if (f == 0 && z == 1) valid = false;
+          if (f > 0) t_out -= 1;
+        }
+        const int Ho = p.shuf_H * 2, Wo = p.shuf_W * 2;
+        const long long pix = (long long)(2 * h + x) * Wo + (2 * w + y);
+        off0 = (long long)(t_out + p.out_t_pad) * p.out_frame_stride + pix * p.ldc +
+               ((n_blk * BLOCK_N) % p.shuf_c);
+        if (p.out_dup_head && t_out == 0) {
+          off_dup1 = off0 - p.out_frame_stride;
+          off_dup2 = off0 - 2 * p.out_frame_stride;
+        }
+        (void)Ho;
+      } else if (p.a_mode == 0) {
+        const int m = m_blk * BLOCK_M + row;
+        valid = m < p.M;
+        off0 = (long long)m * p.ldc + (long long)n_blk * ((p.epi & EPI_SWIGLU) ? BLOCK_N / 2 : BLOCK_N);
+      } else {
+        const int per_frame = p.tiles_w * p.tiles_h;
+        const int t_o = m_blk / per_frame, r = m_blk % per_frame;
+        const int h = (r / p.tiles_w) * p.bh + row / p.bw;
+        const int w = (r % p.tiles_w) * p.bw + row % p.bw;
+        valid = (h < p.H_out) && (w < p.W_out);
+        off0 = (long long)(t_o + p.out_t_pad) * p.out_frame_stride + ((long long)h * p.W_out + w) * p.ldc +
+               (long long)n_blk * BLOCK_N;
+        if (p.out_dup_head && t_o == 0) {
+          off_dup1 = off0 - p.out_frame_stride;
+          off_dup2 = off0 - 2 * p.out_frame_stride;
+        }
+      }
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_STRIDE;
+      const int n_base = n_blk * BLOCK_N;
+
+      if (p.epi & EPI_SWIGLU) {
+        constexpr int HALF = N_OUT / 2;
+#pragma unroll 1
+        for (int c0 = 0; c0 < HALF; c0 += 32) {
+          uint32_t g[32], u[32];
+          tmem_ld32(t_addr + c0, g);
+          tmem_ld32(t_addr + HALF + c0, u);
+          tmem_ld_wait();
+          if (valid) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off0 + c0;
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float g0 = bf16_round(__uint_as_float(g[j])), g1 = bf16_round(__uint_as_float(g[j + 1]));
+              float u0 = bf16_round(__uint_as_float(u[j])), u1 = bf16_round(__uint_as_float(u[j + 1]));
+              pk[j / 2] = pack_bf16x2(bf16_round(silu_f(g0)) * u0, bf16_round(silu_f(g1)) * u1);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<uint4*>(o)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+      } else if (p.epi & EPI_F32) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_OUT; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          if (valid && n_base + c0 < p.N) {
+            float* o = reinterpret_cast<float*>(p.out) + off0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n_base + c0 + j < p.N)
+                *reinterpret_cast<float4*>(o + j) =
+                    make_float4(__uint_as_float(v[j]) * p.out_scale, __uint_as_float(v[j + 1]) * p.out_scale,
+                                __uint_as_float(v[j + 2]) * p.out_scale, __uint_as_float(v[j + 3]) * p.out_scale);
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_OUT; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          if (valid && n_base + c0 < p.N) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            const int n0 = n_base + c0;
+            if (p.epi & EPI_BIAS) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += (n0 + j < p.N) ? __bfloat162float(p.bias[n0 + j]) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
+            if (p.epi & EPI_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = bf16_round(gelu_tanh_f(f[j]));
+            }
+            if (p.epi & EPI_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = bf16_round(silu_f(f[j]));
+            }
+            if (p.epi & EPI_GATE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j] * ((n0 + j < p.N) ? p.gate[n0 + j] : 0.f));
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off0 + c0;
+            if (p.epi & EPI_RESIDUAL) {
+              const __nv_bfloat16* rs = p.residual + off0 + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (n0 + j < p.N) {
+                  uint4 rv = *reinterpret_cast<const uint4*>(rs + j);
+                  const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(&rv);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[j + e] += __bfloat162float(rb[e]);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (n0 + j < p.N) {
+                uint4 pk = make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
+                                      pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
+                *reinterpret_cast<uint4*>(o + j) = pk;
+                if (off_dup1 >= 0) {
+                  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
+                  *reinterpret_cast<uint4*>(ob + off_dup1 + c0 + j) = pk;
+                  *reinterpret_cast<uint4*>(ob + off_dup2 + c0 + j) = pk;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// rank-r bf16 tensor map, dims fastest-first, 128B swizzle, zero OOB fill
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error(SVR2_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[256];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu,%llu box=%u,%u,%u", (int)r,
+             rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
+    return set_error(SVR2_ERR_CUDA, msg);
+  }
+  return SVR2_OK;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+template <int BLOCK_N>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kTotal);
+    if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
+    configured = true;
+  }
+  int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (grid <= 0) return SVR2_OK;
+  gemm_tcgen05_kernel<BLOCK_N><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
+  return SVR2_OK;
+}
+
+static int dispatch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                         cudaStream_t s) {
+  switch (block_n) {
+    case 256: return launch_gemm<256>(ta, tb, p, s);
+    case 128: return launch_gemm<128>(ta, tb, p, s);
+    case 64: return launch_gemm<64>(ta, tb, p, s);
+    case 32: return launch_gemm<32>(ta, tb, p, s);
+    case 16: return launch_gemm<16>(ta, tb, p, s);
+  }
+  return set_error(SVR2_ERR_ARG, "unsupported BLOCK_N");
+}
+
+static int pick_block_n(int N, int epi) {
+  if (epi & EPI_SWIGLU) return 256;
+  if (N >= 256) return 256;
+  if (N > 64) return 128;
+  if (N > 32) return 64;
+  if (N > 16) return 32;
+  return 16;
+}
+
+}  // namespace svr2
+
+using namespace svr2;
+
+// ----------------------------------------------------------------------------
+// C ABI
+// ----------------------------------------------------------------------------
+extern "C" int svr2_linear_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K,
+                                int epi_flags, const void* bias, const float* gate, const void* residual, void* out,
+                                int64_t ldc, float out_scale, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(SVR2_ERR_ARG, "svr2_linear_bf16: empty problem");
+  if ((lda % 8) || (ldw % 8) || (ldc % 8 && !(epi_flags & EPI_F32)) || (N % 8))
+    return set_error(SVR2_ERR_ARG, "svr2_linear_bf16: lda/ldw/ldc/N must be multiples of 8 elements");
+  if ((epi_flags & EPI_SWIGLU) && (N % 256)) return set_error(SVR2_ERR_ARG, "SwiGLU needs N % 256 == 0");
+  const int bn = pick_block_n(N, epi_flags);
+  CUtensorMap ta, tb;
+  uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)lda * 2};
+  uint32_t ba[2] = {BLOCK_K, BLOCK_M};
+  int rc = make_tmap_bf16(&ta, a, 2, da, sa, ba);
+  if (rc) return rc;
+  uint64_t db[2] = {(uint64_t)K, (uint64_t)N}, sb[1] = {(uint64_t)ldw * 2};
+  uint32_t bb[2] = {BLOCK_K, (uint32_t)bn};
+  rc = make_tmap_bf16(&tb, w, 2, db, sb, bb);
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_tiles = (N + bn - 1) / bn;
+  p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  p.a_mode = 0;
+  p.epi = epi_flags & ~EPI_SHUFFLE;
+  p.ldc = (int)ldc;
+  p.out_scale = out_scale;
+  p.bias = (const __nv_bfloat16*)bias;
+  p.gate = gate;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.out = out;
+  if ((p.epi & EPI_BIAS) && !bias) return set_error(SVR2_ERR_ARG, "EPI_BIAS without bias");
+  if ((p.epi & EPI_GATE) && !gate) return set_error(SVR2_ERR_ARG, "EPI_GATE without gate");
+  if ((p.epi & EPI_RESIDUAL) && !residual) return set_error(SVR2_ERR_ARG, "EPI_RESIDUAL without residual");
+  return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream);
+}
+
+// Causal Conv3d as implicit GEMM.  x: NDHWC bf16 with `in_t_pad` halo frames in front
+// (frames [0,in_t_pad) hold the causal context; the first real frame is at index in_t_pad).
+// w: [Cout][kt][kh][kw][Cin] bf16 (K-major).  y: NDHWC bf16 with out_t_pad halo frames.
+extern "C" int svr2_conv3d_bf16(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout, int kt,
+                                int kh, int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags,
+                                const void* bias, const void* residual, void* y, int out_t_pad, int out_dup_head,
+                                int ldc, void* stream) {
+  if (Cin % 64) return set_error(SVR2_ERR_ARG, "svr2_conv3d_bf16: Cin must be a multiple of 64 (pad channels)");
+  if (Cout % 8 || ldc % 8) return set_error(SVR2_ERR_ARG, "svr2_conv3d_bf16: Cout/ldc must be multiples of 8");
+  if (stride_hw != 1 && stride_hw != 2) return set_error(SVR2_ERR_ARG, "stride_hw must be 1 or 2");
+  const int H_out = stride_hw == 1 ? H : H / 2, W_out = stride_hw == 1 ? W : W / 2;
+  if (stride_hw == 2 && ((H | W) & 1)) return set_error(SVR2_ERR_ARG, "stride-2 conv needs even H, W");
+  // tile shape: bw x bh = 128 output pixels
+  int bw = 16, bh = 8;
+  if (W_out >= 128 && H_out < 8) { bw = 128; bh = 1; }
+  else if (W_out <= 8) { bw = 8; bh = 16; }
+  else if (W_out <= 4) { bw = 4; bh = 32; }
+  const int bn = pick_block_n(Cout, 0);
+  CUtensorMap ta, tb;
+  int rc;
+  if (stride_hw == 1) {
+    uint64_t d[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)T_in_total};
+    uint64_t s[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t b[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, 1};
+    rc = make_tmap_bf16(&ta, x, 4, d, s, b);
+  } else {
+    uint64_t d[5] = {(uint64_t)Cin * 2, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)T_in_total};
+    uint64_t s[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 2, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 2};
+    uint32_t b[5] = {BLOCK_K, (uint32_t)bw, 1, (uint32_t)bh, 1};
+    rc = make_tmap_bf16(&ta, x, 5, d, s, b);
+  }
+  if (rc) return rc;
+  const int K = kt * kh * kw * Cin;
+  uint64_t db[2] = {(uint64_t)K, (uint64_t)Cout}, sb[1] = {(uint64_t)K * 2};
+  uint32_t bb[2] = {BLOCK_K, (uint32_t)bn};
+  rc = make_tmap_bf16(&tb, w, 2, db, sb, bb);
+  if (rc) return rc;
+  GemmParams p{};
+  p.a_mode = stride_hw == 1 ? 1 : 2;
+  p.bw = bw; p.bh = bh;
+  p.tiles_w = (W_out + bw - 1) / bw;
+  p.tiles_h = (H_out + bh - 1) / bh;
+  p.taps_t = kt; p.taps_h = kh; p.taps_w = kw;
+  p.cin_blocks = Cin / 64; p.cin = Cin;
+  p.pad_h = p.pad_w = pad_hw;
+  p.stride_t = stride_t;
+  p.H_out = H_out; p.W_out = W_out; p.T_out = T_out;
+  p.M = T_out * p.tiles_w * p.tiles_h * BLOCK_M;
+  p.N = Cout; p.K = K;
+  p.num_m_tiles = T_out * p.tiles_w * p.tiles_h;
+  p.num_n_tiles = (Cout + bn - 1) / bn;
+  p.num_k_blocks = K / BLOCK_K;
+  p.epi = epi_flags & (EPI_BIAS | EPI_RESIDUAL);
+  p.ldc = ldc;
+  p.out_frame_stride = (long long)H_out * W_out * ldc;
+  p.out_t_pad = out_t_pad;
+  p.out_dup_head = out_dup_head;
+  p.bias = (const __nv_bfloat16*)bias;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.out = y;
+  return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream);
+}
+
+// Upsample3D: 1x1x1 conv (GEMM over voxels) with the 3-D pixel shuffle fused into the store.
+// x: [F,H,W,C] bf16 (no halo, contiguous rows); w: [r*C, C]; y: [(F*z - drop) (+pad), 2H, 2W, C].
+extern "C" int svr2_upsample_shuffle_bf16(const void* x, int F, int H, int W, int C, const void* w, const void* bias,
+                                          int temporal, int drop_head, void* y, int out_t_pad, int out_dup_head,
+                                          void* stream) {
+  const int z = temporal ? 2 : 1;
+  const int N = 4 * z * C, M = F * H * W;
+  const int bn = C >= 256 ? 256 : 128;
+  if (C % bn) return set_error(SVR2_ERR_ARG, "svr2_upsample_shuffle_bf16: C must be a multiple of 128");
+  CUtensorMap ta, tb;
+  uint64_t da[2] = {(uint64_t)C, (uint64_t)M}, sa[1] = {(uint64_t)C * 2};
+  uint32_t ba[2] = {BLOCK_K, BLOCK_M};
+  int rc = make_tmap_bf16(&ta, x, 2, da, sa, ba);
+  if (rc) return rc;
+  uint64_t db[2] = {(uint64_t)C, (uint64_t)N}, sb[1] = {(uint64_t)C * 2};
+  uint32_t bb[2] = {BLOCK_K, (uint32_t)bn};
+  rc = make_tmap_bf16(&tb, w, 2, db, sb, bb);
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = C;
+  p.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_tiles = N / bn;
+  p.num_k_blocks = C / BLOCK_K;
+  p.a_mode = 0;
+  p.epi = EPI_SHUFFLE | (bias ? EPI_BIAS : 0);
+  p.ldc = C;
+  p.out_frame_stride = (long long)(2 * H) * (2 * W) * C;
+  p.out_t_pad = out_t_pad;
+  p.out_dup_head = out_dup_head;
+  p.shuf_c = C; p.shuf_z = z; p.shuf_H = H; p.shuf_W = W;
+  p.shuf_drop = (temporal && drop_head) ? 1 : 0;
+  p.bias = (const __nv_bfloat16*)bias;
+  p.out = y;
+  return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream);
+}

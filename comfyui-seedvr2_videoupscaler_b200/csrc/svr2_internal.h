@@ -1,0 +1,23 @@
+// Internal (non-ABI) declarations shared by the .cu files of libsvr2.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/svr2.h"
+
+namespace svr2 {
+int set_error(int code, const char* msg);  // records the message for svr2_last_error(), returns code
+int num_sms();
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    return set_error(SVR2_ERR_CUDA, buf);
+  }
+  return SVR2_OK;
+}
+}  // namespace svr2

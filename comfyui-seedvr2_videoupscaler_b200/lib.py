@@ -1,0 +1,150 @@
+"""ctypes binding of csrc/libsvr2.so (include/svr2.h).
+
+PyTorch tensors supply device memory (`data_ptr()`) and the current stream only.
+There is deliberately no fallback: if the library is missing or a call fails, we raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_double, c_float, c_int, c_int32, c_int64, c_void_p, POINTER
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libsvr2.so")
+
+EPI_BIAS, EPI_GATE, EPI_RESIDUAL, EPI_SWIGLU, EPI_GELU, EPI_F32, EPI_SILU = 1, 2, 4, 8, 16, 32, 128
+
+# name -> argtypes; every function returns int (svr2_status) except svr2_last_error
+_P = c_void_p
+SIGNATURES = {
+    "svr2_version": [],
+    "svr2_device_check": [POINTER(c_int), POINTER(c_int), POINTER(c_int)],
+    "svr2_linear_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, c_float, _P],
+    "svr2_conv3d_bf16": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                         c_int, _P, _P, _P, c_int, c_int, c_int, _P],
+    "svr2_upsample_shuffle_bf16": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_int, c_int, _P],
+    "svr2_attn_varlen_bf16": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
+    "svr2_rmsnorm_ada_bf16": [_P, _P, c_int, c_int, c_float, _P, _P, _P, c_int, _P],
+    "svr2_qk_norm_rope_window_bf16": [_P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_float, c_int, c_int, _P, _P,
+                                      _P, _P],
+    "svr2_txt_window_mean_bf16": [_P, _P, c_int, c_int, c_int, _P],
+    "svr2_patchify_bf16": [_P, _P, c_int, c_int, c_int, c_int, c_int, _P],
+    "svr2_unpatchify_bf16": [_P, c_int, _P, c_int, c_int, c_int, c_int, _P],
+    "svr2_groupnorm_bf16": [_P, _P, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, c_int, _P, _P],
+    "svr2_softmax_rows_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, _P],
+    "svr2_transpose_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, _P],
+    "svr2_ncdhw_to_ndhwc_bf16": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_float, _P],
+    "svr2_ndhwc_to_ncdhw": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
+    "svr2_im2col3_bf16": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
+}
+
+_lib = None
+
+
+class Svr2Error(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Svr2Error(f"{LIB_PATH} not built — run `python __graft_entry__.py` (build()); "
+                            "there is no CPU / PyTorch fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.svr2_last_error.restype = ctypes.c_char_p
+        lib.svr2_last_error.argtypes = []
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = c_int
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise Svr2Error(f"{what} failed ({rc}): {load().svr2_last_error().decode()}")
+
+
+def ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name: str, *args):
+    _check(getattr(load(), name)(*args), name)
+
+
+def device_check():
+    sm, maj, mnr = c_int(), c_int(), c_int()
+    _check(load().svr2_device_check(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr)), "svr2_device_check")
+    return sm.value, maj.value, mnr.value
+
+
+# --------------------------------------------------------------------------
+# thin tensor-level wrappers (shape checks + output allocation only)
+# --------------------------------------------------------------------------
+def _bf16c(t, name):
+    assert t.dtype == torch.bfloat16 and t.is_cuda, f"{name}: bf16 CUDA tensor required"
+    return t
+
+
+def linear(a, w, *, bias=None, gate=None, residual=None, epi=0, out=None, out_scale=1.0, n_valid=None):
+    """out = epi(a @ w^T).  a [M,K] (row stride lda), w [N,K]."""
+    _bf16c(a, "a"), _bf16c(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    if bias is not None:
+        epi |= EPI_BIAS
+    if gate is not None:
+        epi |= EPI_GATE
+        assert gate.dtype == torch.float32
+    if residual is not None:
+        epi |= EPI_RESIDUAL
+    n_out = N // 2 if epi & EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty(M, n_out, device=a.device, dtype=torch.float32 if epi & EPI_F32 else torch.bfloat16)
+    if residual is not None:
+        assert residual.stride(0) == out.stride(0)
+    call("svr2_linear_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epi, ptr(bias), ptr(gate),
+         ptr(residual), ptr(out), out.stride(0), float(out_scale), stream())
+    return out
+
+
+def attn_varlen(q, k, v, cu_seqlens, max_seqlen, out=None, out_row_map=None):
+    _bf16c(q, "q"), _bf16c(k, "k"), _bf16c(v, "v")
+    total, heads, d = q.shape
+    assert d == 128 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    assert cu_seqlens.dtype == torch.int32 and cu_seqlens.is_cuda
+    if out is None:
+        out = torch.empty_like(q)
+    call("svr2_attn_varlen_bf16", ptr(q), ptr(k), ptr(v), ptr(out), ptr(cu_seqlens), cu_seqlens.numel() - 1, total,
+         heads, int(max_seqlen), ptr(out_row_map), stream())
+    return out
+
+
+def rmsnorm_ada(x, scale, shift, *, weight=None, mode=0, eps=1e-5, out=None):
+    _bf16c(x, "x")
+    rows, dim = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    call("svr2_rmsnorm_ada_bf16", ptr(x), ptr(out), rows, dim, float(eps), ptr(weight), ptr(scale), ptr(shift),
+         int(mode), stream())
+    return out
+
+
+def conv3d(x, T_in_total, H, W, Cin, w, Cout, k, stride_t, stride_hw, pad_hw, T_out, y, *, bias=None, residual=None,
+           out_t_pad=0, out_dup_head=0, ldc=None):
+    epi = (EPI_BIAS if bias is not None else 0) | (EPI_RESIDUAL if residual is not None else 0)
+    call("svr2_conv3d_bf16", ptr(x), T_in_total, H, W, Cin, ptr(w), Cout, k[0], k[1], k[2], stride_t, stride_hw,
+         pad_hw, T_out, epi, ptr(bias), ptr(residual), ptr(y), out_t_pad, out_dup_head,
+         int(ldc if ldc is not None else Cout), stream())
+    return y

@@ -1,0 +1,119 @@
+/* libsvr2.so — C ABI of the B200-native SeedVR2 hot path (DiT forward + video-VAE).
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers / sizes and a
+ * CUDA stream handle (`void*` = cudaStream_t, 0 = default stream); no torch types.
+ * All work is stream-ordered, no hidden synchronisation, no CPU fallback.
+ * Return value: SVR2_OK (0) or a negative svr2_status; the message is available
+ * from svr2_last_error() (thread-local).  Caller owns every buffer.
+ *
+ * bf16 = __nv_bfloat16 (torch.bfloat16) unless stated.  "Reference" citations are
+ * file:line under numz/ComfyUI-SeedVR2_VideoUpscaler @ 4490bd1 — the Python
+ * call each entry point replaces (the reference has no FFI of its own; see
+ * INTEGRATION.md for the ctypes binding a maintainer would add).
+ */
+#ifndef SVR2_H_
+#define SVR2_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum svr2_status {
+  SVR2_OK = 0,
+  SVR2_ERR_ARG = -1,   /* invalid argument / unsupported shape */
+  SVR2_ERR_CUDA = -2,  /* CUDA runtime / driver error */
+  SVR2_ERR_ARCH = -3,  /* device is not sm_100 */
+};
+
+/* epilogue flags of svr2_linear_bf16 / svr2_conv3d_bf16 (applied in this order,
+ * each step rounded to bf16 where the reference's bf16 path rounds) */
+enum svr2_epilogue {
+  SVR2_EPI_BIAS = 1,      /* + bias[n]                                   nn.Linear / Conv3d bias              */
+  SVR2_EPI_GATE = 2,      /* * gate[n] (fp32)                            AdaSingle "out", modulation.py:109-116 */
+  SVR2_EPI_RESIDUAL = 4,  /* + residual[m,n]                             mmsr_block.py:113-114,125-126         */
+  SVR2_EPI_SWIGLU = 8,    /* silu(acc[:, j]) * acc[:, j+128] per 256-col tile (weights interleaved) mlp.py:60-62 */
+  SVR2_EPI_GELU = 16,     /* gelu_tanh                                   dit_7b/mlp.py:35-43                   */
+  SVR2_EPI_F32 = 32,      /* fp32 output = acc * out_scale (attention scores)                                  */
+  SVR2_EPI_SILU = 128,    /* silu                                        embedding.py:56-60                    */
+};
+
+const char* svr2_last_error(void);
+int svr2_version(void);
+/* fills sm count / major / minor of the current device; SVR2_ERR_ARCH unless sm_100 */
+int svr2_device_check(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1: Linear.  out[M,N] = epi(a[M,K] @ w[N,K]^T).  Replaces nn.Linear at
+ * dit_3b/nablocks/attention/mmattn.py:56-59,173,269; dit_3b/mlp.py:56-61; dit_7b/mlp.py:35-43;
+ * dit_3b/patch/patch_v1.py:37,62; dit_3b/embedding.py:38-40; diffusers Attention to_q/k/v/out
+ * (attn_video_vae.py:612-632).  lda/ldw/ldc in elements, multiples of 8. */
+int svr2_linear_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K, int epi_flags,
+                     const void* bias, const float* gate, const void* residual, void* out, int64_t ldc,
+                     float out_scale, void* stream);
+
+/* ---- K6: causal Conv3d (implicit GEMM).  Replaces InflatedCausalConv3d.forward
+ * (video_vae_v3/modules/causal_inflation_lib.py:213-305) incl. Downsample3D's (0,1,0,1) pad
+ * (attn_video_vae.py:242-244).  x: [T_in_total,H,W,Cin] NDHWC, the causal halo frames are real
+ * frames at the front of x; w: [Cout][kt][kh][kw][Cin]; y: [out_t_pad+T_out,Ho,Wo,ldc]. */
+int svr2_conv3d_bf16(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout, int kt, int kh,
+                     int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags, const void* bias,
+                     const void* residual, void* y, int out_t_pad, int out_dup_head, int ldc, void* stream);
+
+/* ---- Upsample3D: 1x1x1 conv + 'b (x y z c) f h w -> b c (f z) (h x) (w y)' + remove_head
+ * (attn_video_vae.py:135-153, causal_inflation_lib.py:412-419) in one GEMM. */
+int svr2_upsample_shuffle_bf16(const void* x, int F, int H, int W, int C, const void* w, const void* bias,
+                               int temporal, int drop_head, void* y, int out_t_pad, int out_dup_head, void* stream);
+
+/* ---- K4: varlen (windowed) self-attention, head_dim 128, non-causal, scale 1/sqrt(128).
+ * Drop-in for FlashAttentionVarlen.forward / pytorch_varlen_attention (dit_3b/attention.py:27-64,
+ * 114-148): q,k,v,out [total, heads, 128] bf16, cu_seqlens int32 [n_seq+1] (device).
+ * out_row_map (optional, device int32 [total]): output row r is written to row out_row_map[r]
+ * (fuses window_reverse, mmattn.py:264). */
+int svr2_attn_varlen_bf16(const void* q, const void* k, const void* v, void* out, const int32_t* cu_seqlens,
+                          int n_seq, int total, int heads, int max_seqlen, const int32_t* out_row_map,
+                          void* stream);
+
+/* ---- K2: RMSNorm (+optional affine) + AdaSingle "in".  CustomRMSNorm.forward
+ * (dit_3b/normalization.py:88-109) + AdaSingle.forward (modulation.py:109-111).
+ * mode 0: y = bf16((rms(x)*w) * scale + shift)          (attention branch / output head)
+ * mode 1: y = bf16(bf16(bf16(rms(x)) * scale) + shift)  (MLP branch, mmsr_block.py:117-122) */
+int svr2_rmsnorm_ada_bf16(const void* x, void* y, int rows, int dim, float eps, const float* weight,
+                          const float* scale, const float* shift, int mode, void* stream);
+
+/* ---- q/k RMSNorm(128, affine) + 3-axis RoPE + window partition + per-window text concat
+ * (mmattn.py:199-248, rope.py:116-176, na.py:320-424).  qkv_vid [L,3*heads*128], qkv_txt [l,...];
+ * row_src[total]: >=0 video token index, <0: -(text index+1); row_rope[total*3]: rows of the
+ * cos/sin tables per axis (or -1 = no rotation); tables [R][nfreq] fp32. */
+int svr2_qk_norm_rope_window_bf16(const void* qkv_vid, const void* qkv_txt, const int32_t* row_src,
+                                  const int32_t* row_rope, const float* cos_tab, const float* sin_tab, int nfreq,
+                                  const float* wq_vid, const float* wk_vid, const float* wq_txt, const float* wk_txt,
+                                  float eps, int total, int heads, void* q, void* k, void* v, void* stream);
+
+/* mean over windows of the text rows (na.py:396-417): in [n_win, l, dim] -> out [l, dim] */
+int svr2_txt_window_mean_bf16(const void* in, void* out, int n_win, int l, int dim, void* stream);
+
+/* NaPatchIn / NaPatchOut rearranges (patch_v1.py:76-127), patch (1,2,2) */
+int svr2_patchify_bf16(const void* vid, void* out, int T, int H, int W, int C, int ld_out, void* stream);
+int svr2_unpatchify_bf16(const void* in, int ld_in, void* out, int T, int H, int W, int C, void* stream);
+
+/* ---- K7: per-frame GroupNorm(32) (+SiLU).  causal_norm_wrapper
+ * (causal_inflation_lib.py:354-409) + nn.SiLU.  x,y: [F,HW,C] NDHWC; stats: double [F,32,2] scratch. */
+int svr2_groupnorm_bf16(const void* x, void* y, int frames, int hw, int C, const void* gamma, const void* beta,
+                        float eps, int silu, int out_t_pad, int out_dup_head, double* stats, void* stream);
+
+/* row softmax fp32 -> bf16 (VAE mid-block attention, attn_video_vae.py:656-668) */
+int svr2_softmax_rows_bf16(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, void* stream);
+int svr2_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols, void* stream);
+
+/* layout glue (optimization/performance.py:12-166): NCDHW any-float <-> NDHWC bf16 with halo / channel pad */
+int svr2_ncdhw_to_ndhwc_bf16(const void* in, int in_dtype, int C, int T, int H, int W, void* out, int C_pad,
+                             int out_t_pad, float div, void* stream);
+int svr2_ndhwc_to_ncdhw(const void* in, int ld_in, int C, int T, int H, int W, void* out, int out_dtype,
+                        void* stream);
+/* 3x3x3 im2col for the 3-channel encoder conv_in: x [2+T,H,W,Cpad] -> out [T*H*W, ld_out] (81 real cols) */
+int svr2_im2col3_bf16(const void* x, int T, int H, int W, int C, int ld_in, void* out, int ld_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVR2_H_ */
