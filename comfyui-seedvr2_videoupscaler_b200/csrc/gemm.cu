@@ -473,8 +473,9 @@ extern "C" int svr2_linear_bf16(const void* a, int64_t lda, const void* w, int64
                                 int epi_flags, const void* bias, const float* gate, const void* residual, void* out,
                                 int64_t ldc, float out_scale, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(SVR2_ERR_ARG, "svr2_linear_bf16: empty problem");
-  if ((lda % 8) || (ldw % 8) || (ldc % 8 && !(epi_flags & EPI_F32)) || (N % 8))
-    return set_error(SVR2_ERR_ARG, "svr2_linear_bf16: lda/ldw/ldc/N must be multiples of 8 elements");
+  const bool f32 = (epi_flags & EPI_F32) != 0;
+  if ((lda % 8) || (ldw % 8) || (ldc % (f32 ? 4 : 8)) || (N % (f32 ? 4 : 8)))
+    return set_error(SVR2_ERR_ARG, "svr2_linear_bf16: lda/ldw must be multiples of 8, ldc/N of 8 (4 for fp32 out)");
   if ((epi_flags & EPI_SWIGLU) && (N % 256)) return set_error(SVR2_ERR_ARG, "SwiGLU needs N % 256 == 0");
   const int bn = pick_block_n(N, epi_flags);
   CUtensorMap ta, tb;

@@ -1,0 +1,291 @@
+"""Host side of the B200 causal 3-D conv video VAE (encode + decode).
+
+Mirrors the reference operator interface
+``VideoAutoencoderKLWrapper.encode(x).latent`` / ``.decode(z).sample``
+(reference ``src/models/video_vae_v3/modules/attn_video_vae.py:1680-1698``) and
+replaces ``Encoder3D`` (``:808-856``), ``Decoder3D`` (``:983-1035``),
+``ResnetBlock3D`` (``:311-362``), ``Upsample3D`` (``:110-174``), ``Downsample3D``
+(``:226-250``), ``UNetMidBlock3D`` + diffusers ``Attention`` (``:656-668``),
+``InflatedCausalConv3d`` and ``causal_norm_wrapper``
+(``causal_inflation_lib.py:213-305, 354-409``) with calls into libsvr2.so.
+
+Data layout: activations are NDHWC bf16.  A tensor that feeds a causal 3x3x3
+conv carries its temporal halo as two real frames in front of frame 0
+(``pad = 2``); the kernel that produces it writes frame 0 into the halo as well
+(first-frame replication, ``extend_head``, ``causal_inflation_lib.py:423-438``).
+The reference's temporal slicing (``slicing_encode/_decode``, ``:1254-1300``) is
+numerically exact, so the whole clip is processed un-sliced here.
+"""
+from __future__ import annotations
+
+from ctypes import c_void_p
+from typing import Dict, Optional
+
+import torch
+
+from . import lib
+
+
+class Act:
+    """[pad + T, H, W, C] bf16 activation; ``pad`` halo frames replicate frame 0."""
+
+    def __init__(self, T, H, W, C, pad, device, buf=None):
+        self.T, self.H, self.W, self.C, self.pad = T, H, W, C, pad
+        self.buf = buf if buf is not None else torch.empty(pad + T, H, W, C, device=device, dtype=torch.bfloat16)
+
+    def without_halo(self):
+        return self if self.pad == 0 else Act(self.T, self.H, self.W, self.C, 0, None, buf=self.body)
+
+    @property
+    def frame_elems(self):
+        return self.H * self.W * self.C
+
+    def body_ptr(self):
+        return self.buf.data_ptr() + self.pad * self.frame_elems * 2
+
+    @property
+    def body(self):
+        return self.buf[self.pad:]
+
+
+class VAEOutput:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class B200VideoVAE:
+    """Drop-in for the reference ``runner.vae`` (model-slot seam, infer.py:125-266)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda"):
+        lib.device_check()
+        self.device = torch.device(device)
+        self.W: Dict[str, torch.Tensor] = {}
+        self._load(state_dict)
+        self._stats = None
+
+    # ---- weights ---------------------------------------------------------
+    def _conv_w(self, w, cin_pad=None, cout_pad=None):
+        """[O,I,kt,kh,kw] -> [O, kt*kh*kw*I] bf16 (K-major, tap-major then channel)."""
+        O, I = w.shape[:2]
+        w = w.to(self.device, torch.bfloat16).permute(0, 2, 3, 4, 1)  # O,kt,kh,kw,I
+        if cin_pad and cin_pad > I:
+            w = torch.nn.functional.pad(w, (0, cin_pad - I))
+        w = w.reshape(O, -1)
+        if cout_pad and cout_pad > O:
+            w = torch.nn.functional.pad(w, (0, 0, 0, cout_pad - O))
+        return w.contiguous()
+
+    def _vec(self, v, pad_to=None):
+        v = v.to(self.device, torch.bfloat16)
+        if pad_to and pad_to > v.numel():
+            v = torch.nn.functional.pad(v, (0, pad_to - v.numel()))
+        return v.contiguous()
+
+    def _load(self, sd):
+        sd = dict(sd)
+        # deprecated diffusers attention key names (attn_video_vae.py:1647-1657)
+        for k in list(sd.keys()):
+            for old, new in ((".query.", ".to_q."), (".key.", ".to_k."), (".value.", ".to_v."),
+                             (".proj_attn.", ".to_out.0.")):
+                if ".attentions." in k and old in k:
+                    sd[k.replace(old, new)] = sd.pop(k)
+                    break
+        W = self.W
+        for k, v in sd.items():
+            if k.endswith("upscale_conv.weight"):
+                W[k] = v.to(self.device, torch.bfloat16).reshape(v.shape[0], v.shape[1]).contiguous()
+            elif k == "encoder.conv_in.weight":      # im2col GEMM: K = 81 padded to 128
+                W[k] = torch.nn.functional.pad(self._conv_w(v), (0, 128 - 81)).contiguous()
+            elif k == "decoder.conv_in.weight":
+                W[k] = self._conv_w(v, cin_pad=64)
+            elif k == "decoder.conv_out.weight":
+                W[k] = self._conv_w(v, cout_pad=8)
+            elif k == "decoder.conv_out.bias":
+                W[k] = self._vec(v, 8)
+            elif k.endswith(".weight") and v.ndim == 5:
+                W[k] = self._conv_w(v)
+            elif k.endswith(".weight") and v.ndim == 4:   # 2-D checkpoint: "tail" inflation (causal_inflation_lib.py:440-457)
+                raise NotImplementedError("2-D VAE checkpoints are not supported by the B200 engine")
+            else:
+                W[k] = self._vec(v) if v.ndim == 1 else v.to(self.device, torch.bfloat16).contiguous()
+            if k.endswith(".weight") and v.ndim == 5:
+                W[k + ".k"] = tuple(v.shape[2:])
+
+    def parameters(self):
+        return iter(self.W[k] for k in self.W if not k.endswith(".k"))
+
+    def to(self, *a, **k):
+        return self
+
+    # ---- primitive wrappers ----------------------------------------------
+    def _gn(self, x: Act, prefix: str, silu: bool, pad: int) -> Act:
+        y = Act(x.T, x.H, x.W, x.C, pad, self.device)
+        if self._stats is None or self._stats.numel() < x.T * 64:
+            self._stats = torch.empty(max(x.T, 64) * 64, device=self.device, dtype=torch.float64)
+        lib.call("svr2_groupnorm_bf16", c_void_p(x.body_ptr()), lib.ptr(y.buf), x.T, x.H * x.W, x.C,
+                 lib.ptr(self.W[prefix + ".weight"]), lib.ptr(self.W[prefix + ".bias"]), 1e-6, int(silu), pad,
+                 int(pad > 0), lib.ptr(self._stats), lib.stream())
+        return y
+
+    def _conv(self, x: Act, prefix: str, *, out_pad=0, residual: Optional[Act] = None, stride_t=1, stride_hw=1,
+              cout=None, cin=None) -> Act:
+        w = self.W[prefix + ".weight"]
+        kt, kh, kw = self.W[prefix + ".weight.k"]
+        Cout = cout if cout is not None else w.shape[0]
+        Cin = cin if cin is not None else x.C
+        assert x.pad == kt - 1, f"{prefix}: conv with kt={kt} needs a {kt - 1}-frame halo, got {x.pad}"
+        T_out = (x.T - 1) // stride_t + 1
+        Ho, Wo = (x.H, x.W) if stride_hw == 1 else (x.H // 2, x.W // 2)
+        y = Act(T_out, Ho, Wo, w.shape[0], out_pad, self.device)
+        res_ptr = None
+        if residual is not None:
+            assert (residual.T, residual.H, residual.W, residual.C) == (T_out, Ho, Wo, w.shape[0])
+            # the kernel indexes the residual with the output's offsets (which include out_pad halo frames)
+            res_ptr = c_void_p(residual.body_ptr() - out_pad * y.frame_elems * 2)
+        epi = lib.EPI_BIAS | (lib.EPI_RESIDUAL if residual is not None else 0)
+        pad_hw = 1 if (stride_hw == 1 and kh == 3) else 0
+        lib.call("svr2_conv3d_bf16", lib.ptr(x.buf), x.pad + x.T, x.H, x.W, Cin, lib.ptr(w), w.shape[0], kt, kh, kw,
+                 stride_t, stride_hw, pad_hw, T_out, epi, lib.ptr(self.W[prefix + ".bias"]), res_ptr, lib.ptr(y.buf),
+                 out_pad, int(out_pad > 0), w.shape[0], lib.stream())
+        return y
+
+    def _resnet(self, x: Act, p: str, out_pad=0) -> Act:
+        """ResnetBlock3D.forward (attn_video_vae.py:311-362)."""
+        h = self._gn(x, p + "norm1", True, 2)
+        h = self._conv(h, p + "conv1")
+        h = self._gn(h, p + "norm2", True, 2)
+        if (p + "conv_shortcut.weight") in self.W:
+            sc = self._conv(x.without_halo(), p + "conv_shortcut")
+        else:
+            sc = x
+        return self._conv(h, p + "conv2", out_pad=out_pad, residual=sc)
+
+    def _attention(self, x: Act, p: str) -> Act:
+        """UNetMidBlock3D per-frame attention (attn_video_vae.py:656-668): GN -> q,k,v -> 1-head
+        softmax(q k^T / sqrt(C)) v -> out proj -> + x."""
+        C, n = x.C, x.H * x.W
+        dev = self.device
+        y = self._gn(x, p + "group_norm", False, 0)
+        yf = y.buf.view(x.T * n, C)
+        q = lib.linear(yf, self.W[p + "to_q.weight"], bias=self.W[p + "to_q.bias"])
+        k = lib.linear(yf, self.W[p + "to_k.weight"], bias=self.W[p + "to_k.bias"])
+        v = lib.linear(yf, self.W[p + "to_v.weight"], bias=self.W[p + "to_v.bias"])
+        del y, yf
+        ldn = (n + 7) // 8 * 8
+        cq = max(128, min(n, (1 << 28) // max(n, 1)) // 128 * 128)   # S chunk <= 1 GiB fp32
+        cq = min(cq, (n + 127) // 128 * 128)
+        vt = torch.empty(C, ldn, device=dev, dtype=torch.bfloat16)
+        S = torch.empty(min(cq, n), n, device=dev, dtype=torch.float32)
+        P = torch.empty(min(cq, n), ldn, device=dev, dtype=torch.bfloat16)
+        o = torch.empty(x.T * n, C, device=dev, dtype=torch.bfloat16)
+        scale = 1.0 / (C ** 0.5)
+        for f in range(x.T):
+            qf, kf, vf = q[f * n:(f + 1) * n], k[f * n:(f + 1) * n], v[f * n:(f + 1) * n]
+            lib.call("svr2_transpose_bf16", lib.ptr(vf), C, lib.ptr(vt), ldn, n, C, lib.stream())
+            for r0 in range(0, n, cq):
+                rows = min(cq, n - r0)
+                lib.linear(qf[r0:r0 + rows], kf, epi=lib.EPI_F32, out=S[:rows], out_scale=scale)
+                lib.call("svr2_softmax_rows_bf16", lib.ptr(S), n, lib.ptr(P), ldn, rows, n, lib.stream())
+                lib.linear(P[:rows, :n], vt[:, :n], out=o[f * n + r0: f * n + r0 + rows])
+        out = Act(x.T, x.H, x.W, C, 0, dev)
+        xb = x.body.reshape(x.T * n, C)
+        lib.linear(o, self.W[p + "to_out.0.weight"], bias=self.W[p + "to_out.0.bias"], residual=xb,
+                   out=out.buf.view(x.T * n, C))
+        return out
+
+    def _mid(self, x: Act, p: str) -> Act:
+        x = self._resnet(x, p + "resnets.0.")
+        x = self._attention(x, p + "attentions.0.")
+        return self._resnet(x, p + "resnets.1.")
+
+    def _upsample(self, x: Act, p: str, temporal: bool) -> Act:
+        """Upsample3D.forward (attn_video_vae.py:110-174)."""
+        z = 2 if temporal else 1
+        T_out = x.T * z - (1 if temporal else 0)
+        y = Act(T_out, 2 * x.H, 2 * x.W, x.C, 2, self.device)
+        lib.call("svr2_upsample_shuffle_bf16", c_void_p(x.body_ptr()), x.T, x.H, x.W, x.C,
+                 lib.ptr(self.W[p + "upscale_conv.weight"]), lib.ptr(self.W[p + "upscale_conv.bias"]), int(temporal), 1,
+                 lib.ptr(y.buf), 2, 1, lib.stream())
+        return self._conv(y, p + "conv")
+
+    # ---- public API --------------------------------------------------------
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, return_dict=True, tiled=False, tile_size=None, tile_overlap=None):
+        """z (1,16,T,h,w) or (1,16,h,w) -> .sample (1,3,4T-3,8h,8w) bf16 (Decoder3D.forward)."""
+        if tiled:
+            raise NotImplementedError("tiled VAE decode changes results (SURVEY.md a25) and is not part of the B200 path")
+        squeeze = z.ndim == 4
+        if squeeze:
+            z = z.unsqueeze(2)
+        assert z.shape[0] == 1 and z.shape[1] == 16
+        _, _, T, h, w = z.shape
+        dev = self.device
+        zin = z[0].to(dev).contiguous()
+        dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[zin.dtype]
+        x = Act(T, h, w, 64, 2, dev)
+        lib.call("svr2_ncdhw_to_ndhwc_bf16", lib.ptr(zin), dt, 16, T, h, w, lib.ptr(x.buf), 64, 2, 1.0, lib.stream())
+        x = self._conv(x, "decoder.conv_in")
+        x = self._mid(x, "decoder.mid_block.")
+        for i in range(4):
+            for j in range(3):
+                x = self._resnet(x, f"decoder.up_blocks.{i}.resnets.{j}.")
+            if i < 3:
+                x = self._upsample(x, f"decoder.up_blocks.{i}.upsamplers.0.", temporal=i < 2)
+        x = self._gn(x, "decoder.conv_norm_out", True, 2)
+        x = self._conv(x, "decoder.conv_out")
+        out = torch.empty(1, 3, x.T, x.H, x.W, device=dev, dtype=torch.bfloat16)
+        lib.call("svr2_ndhwc_to_ncdhw", lib.ptr(x.buf), 8, 3, x.T, x.H, x.W, lib.ptr(out), 1, lib.stream())
+        if squeeze:
+            out = out.squeeze(2)
+        return VAEOutput(sample=out)
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, return_dict=True, tiled=False, tile_size=None, tile_overlap=None):
+        """x (1,3,T,H,W) or (1,3,H,W) in [-1,1] -> .latent (1,16,(T-1)/4+1,H/8,W/8) bf16 = posterior mode
+        (Encoder3D.forward + DiagonalGaussianDistribution.mode, attn_video_vae.py:1680-1689)."""
+        if tiled:
+            raise NotImplementedError("tiled VAE encode is not part of the B200 path")
+        squeeze = x.ndim == 4
+        if squeeze:
+            x = x.unsqueeze(2)
+        assert x.shape[0] == 1 and x.shape[1] == 3
+        _, _, T, H, Wd = x.shape
+        dev = self.device
+        xin = x[0].to(dev).contiguous()
+        dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[xin.dtype]
+        x8 = torch.empty(2 + T, H, Wd, 8, device=dev, dtype=torch.bfloat16)
+        lib.call("svr2_ncdhw_to_ndhwc_bf16", lib.ptr(xin), dt, 3, T, H, Wd, lib.ptr(x8), 8, 2, 1.0, lib.stream())
+        col = torch.empty(T * H * Wd, 128, device=dev, dtype=torch.bfloat16)
+        lib.call("svr2_im2col3_bf16", lib.ptr(x8), T, H, Wd, 3, 8, lib.ptr(col), 128, lib.stream())
+        h = Act(T, H, Wd, 128, 0, dev)
+        lib.linear(col, self.W["encoder.conv_in.weight"], bias=self.W["encoder.conv_in.bias"],
+                   out=h.buf.view(T * H * Wd, 128))
+        del col, x8
+        for i in range(4):
+            p = f"encoder.down_blocks.{i}."
+            temporal = i in (1, 2)
+            h = self._resnet(h, p + "resnets.0.")
+            h = self._resnet(h, p + "resnets.1.", out_pad=2 if (i < 3 and temporal) else 0)
+            if i < 3:
+                h = self._conv(h, p + "downsamplers.0.conv", stride_t=2 if temporal else 1, stride_hw=2)
+        h = self._mid(h, "encoder.mid_block.")
+        h = self._gn(h, "encoder.conv_norm_out", True, 2)
+        h = self._conv(h, "encoder.conv_out")
+        out = torch.empty(1, 16, h.T, h.H, h.W, device=dev, dtype=torch.bfloat16)
+        lib.call("svr2_ndhwc_to_ncdhw", lib.ptr(h.buf), 32, 16, h.T, h.H, h.W, lib.ptr(out), 1, lib.stream())
+        if squeeze:
+            out = out.squeeze(2)
+        return VAEOutput(latent=out, latent_dist=None)
+
+    # reference wrapper surface used by the pipeline (model_configuration.py:1247-1276)
+    def preprocess(self, x):
+        return x
+
+    def postprocess(self, x):
+        return x
+
+    def set_causal_slicing(self, *, split_size=None, memory_device=None):
+        pass  # slicing is exact in the reference; the engine chooses its own chunking
+
+    def set_memory_limit(self, conv_max_mem=None, norm_max_mem=None):
+        pass
