@@ -93,6 +93,7 @@ class WindowLayout:
     row_src: torch.Tensor      # int32 [total]   >=0 video token, <0 -(text idx + 1)
     row_rope: torch.Tensor     # int32 [total,3] rows of the cos/sin tables (or -1)
     out_row_map: torch.Tensor  # int32 [total]   video rows -> token idx, text rows -> L + w*l + j
+    attn_flops: float = 0.0    # sum over windows of 4 * len^2 * 128 (per head)
 
 
 def build_layout(T: int, Hp: int, Wp: int, l: int, shifted: bool, variant: str, device) -> Tuple[WindowLayout, dict]:
@@ -130,7 +131,8 @@ def build_layout(T: int, Hp: int, Wp: int, l: int, shifted: bool, variant: str, 
     lay = WindowLayout(
         n_win=len(boxes), total=int(lens_t.sum()), max_len=int(lens_t.max()),
         cu_seqlens=cu.to(device), row_src=torch.cat(src).int().to(device),
-        row_rope=torch.cat(rope).int().contiguous().to(device), out_row_map=torch.cat(omap).int().to(device))
+        row_rope=torch.cat(rope).int().contiguous().to(device), out_row_map=torch.cat(omap).int().to(device),
+        attn_flops=float((lens_t.double() ** 2).sum()) * 4 * 128)
     return lay, size_rows
 
 
@@ -327,7 +329,8 @@ class B200NaDiT:
                      lay.total, heads, lib.ptr(q), lib.ptr(kk), lib.ptr(v), st)
             del qkv_v
             o_view = o_all.view(-1, heads, 128)
-            lib.attn_varlen(q, kk, v, lay.cu_seqlens, lay.max_len, out=o_view, out_row_map=lay.out_row_map)
+            lib.attn_varlen(q, kk, v, lay.cu_seqlens, lay.max_len, out=o_view, out_row_map=lay.out_row_map,
+                            flops=lay.attn_flops * heads)
             lib.call("svr2_txt_window_mean_bf16", lib.ptr(o_all[L:]), lib.ptr(o_t), lay.n_win, l, inner, st)
             h_v = lib.linear(o_all[:L], k("vid", "out.w"), bias=k("vid", "out.b"), gate=m("vid.attn_gate"), residual=x)
             h_t = lib.linear(o_t, k("txt", "out.w"), bias=k("txt", "out.b"),

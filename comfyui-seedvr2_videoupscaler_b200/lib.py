@@ -77,8 +77,50 @@ def stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def call(name: str, *args):
-    _check(getattr(load(), name)(*args), name)
+# kernels launched per C-ABI call (for the bench's gpu_launches count)
+KERNELS_PER_CALL = {"svr2_groupnorm_bf16": 2}
+
+
+class Profiler:
+    """Optional per-call CUDA-event timing on the launching stream (bench.py roofline).
+    Off by default: `lib.PROFILER = Profiler()` turns it on."""
+
+    def __init__(self):
+        self.records = []      # (name, flops, bytes, start_event, end_event)
+        self.launches = 0
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+    def reset(self):
+        self.records.clear()
+        self.launches = 0
+
+
+PROFILER = None
+LAUNCHES = 0
+
+
+def call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0):
+    global LAUNCHES
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
+    prof = PROFILER
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(getattr(load(), name)(*args), name)
+        e1.record()
+        prof.records.append((name, flops, nbytes, e0, e1))
+    else:
+        _check(getattr(load(), name)(*args), name)
 
 
 def device_check():
@@ -114,11 +156,12 @@ def linear(a, w, *, bias=None, gate=None, residual=None, epi=0, out=None, out_sc
     if residual is not None:
         assert residual.stride(0) == out.stride(0)
     call("svr2_linear_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epi, ptr(bias), ptr(gate),
-         ptr(residual), ptr(out), out.stride(0), float(out_scale), stream())
+         ptr(residual), ptr(out), out.stride(0), float(out_scale), stream(),
+         flops=2.0 * M * (n_valid if n_valid is not None else N) * K)
     return out
 
 
-def attn_varlen(q, k, v, cu_seqlens, max_seqlen, out=None, out_row_map=None):
+def attn_varlen(q, k, v, cu_seqlens, max_seqlen, out=None, out_row_map=None, flops=0.0):
     _bf16c(q, "q"), _bf16c(k, "k"), _bf16c(v, "v")
     total, heads, d = q.shape
     assert d == 128 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
@@ -126,7 +169,7 @@ def attn_varlen(q, k, v, cu_seqlens, max_seqlen, out=None, out_row_map=None):
     if out is None:
         out = torch.empty_like(q)
     call("svr2_attn_varlen_bf16", ptr(q), ptr(k), ptr(v), ptr(out), ptr(cu_seqlens), cu_seqlens.numel() - 1, total,
-         heads, int(max_seqlen), ptr(out_row_map), stream())
+         heads, int(max_seqlen), ptr(out_row_map), stream(), flops=float(flops))
     return out
 
 
@@ -137,7 +180,7 @@ def rmsnorm_ada(x, scale, shift, *, weight=None, mode=0, eps=1e-5, out=None):
     if out is None:
         out = torch.empty_like(x)
     call("svr2_rmsnorm_ada_bf16", ptr(x), ptr(out), rows, dim, float(eps), ptr(weight), ptr(scale), ptr(shift),
-         int(mode), stream())
+         int(mode), stream(), nbytes=4.0 * rows * dim)
     return out
 
 
@@ -146,5 +189,6 @@ def conv3d(x, T_in_total, H, W, Cin, w, Cout, k, stride_t, stride_hw, pad_hw, T_
     epi = (EPI_BIAS if bias is not None else 0) | (EPI_RESIDUAL if residual is not None else 0)
     call("svr2_conv3d_bf16", ptr(x), T_in_total, H, W, Cin, ptr(w), Cout, k[0], k[1], k[2], stride_t, stride_hw,
          pad_hw, T_out, epi, ptr(bias), ptr(residual), ptr(y), out_t_pad, out_dup_head,
-         int(ldc if ldc is not None else Cout), stream())
+         int(ldc if ldc is not None else Cout), stream(),
+         flops=2.0 * T_out * (H // stride_hw) * (W // stride_hw) * Cout * k[0] * k[1] * k[2] * Cin)
     return y

@@ -110,9 +110,10 @@ class B200VideoVAE:
                 W[k] = self._vec(v) if v.ndim == 1 else v.to(self.device, torch.bfloat16).contiguous()
             if k.endswith(".weight") and v.ndim == 5:
                 W[k + ".k"] = tuple(v.shape[2:])
+                W[k + ".real"] = (v.shape[0], v.shape[1])   # un-padded (Cout, Cin) for the FLOP model
 
     def parameters(self):
-        return iter(self.W[k] for k in self.W if not k.endswith(".k"))
+        return iter(v for v in self.W.values() if torch.is_tensor(v))
 
     def to(self, *a, **k):
         return self
@@ -124,7 +125,7 @@ class B200VideoVAE:
             self._stats = torch.empty(max(x.T, 64) * 64, device=self.device, dtype=torch.float64)
         lib.call("svr2_groupnorm_bf16", c_void_p(x.body_ptr()), lib.ptr(y.buf), x.T, x.H * x.W, x.C,
                  lib.ptr(self.W[prefix + ".weight"]), lib.ptr(self.W[prefix + ".bias"]), 1e-6, int(silu), pad,
-                 int(pad > 0), lib.ptr(self._stats), lib.stream())
+                 int(pad > 0), lib.ptr(self._stats), lib.stream(), nbytes=6.0 * x.T * x.H * x.W * x.C)
         return y
 
     def _conv(self, x: Act, prefix: str, *, out_pad=0, residual: Optional[Act] = None, stride_t=1, stride_hw=1,
@@ -146,7 +147,9 @@ class B200VideoVAE:
         pad_hw = 1 if (stride_hw == 1 and kh == 3) else 0
         lib.call("svr2_conv3d_bf16", lib.ptr(x.buf), x.pad + x.T, x.H, x.W, Cin, lib.ptr(w), w.shape[0], kt, kh, kw,
                  stride_t, stride_hw, pad_hw, T_out, epi, lib.ptr(self.W[prefix + ".bias"]), res_ptr, lib.ptr(y.buf),
-                 out_pad, int(out_pad > 0), w.shape[0], lib.stream())
+                 out_pad, int(out_pad > 0), w.shape[0], lib.stream(),
+                 flops=2.0 * T_out * Ho * Wo * self.W[prefix + ".weight.real"][0] * kt * kh * kw
+                 * self.W[prefix + ".weight.real"][1])
         return y
 
     def _resnet(self, x: Act, p: str, out_pad=0) -> Act:
@@ -205,7 +208,7 @@ class B200VideoVAE:
         y = Act(T_out, 2 * x.H, 2 * x.W, x.C, 2, self.device)
         lib.call("svr2_upsample_shuffle_bf16", c_void_p(x.body_ptr()), x.T, x.H, x.W, x.C,
                  lib.ptr(self.W[p + "upscale_conv.weight"]), lib.ptr(self.W[p + "upscale_conv.bias"]), int(temporal), 1,
-                 lib.ptr(y.buf), 2, 1, lib.stream())
+                 lib.ptr(y.buf), 2, 1, lib.stream(), flops=2.0 * x.T * x.H * x.W * x.C * 4 * z * x.C)
         return self._conv(y, p + "conv")
 
     # ---- public API --------------------------------------------------------
