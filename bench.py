@@ -194,7 +194,7 @@ def main():
     def step(src):
         y = eng.upscale_clip(src, noise=noise, seed=42)
         if world > 1:
-            dist.all_gather_into_tensor(gather_buf.view(world, -1), y.reshape(-1).contiguous())
+            dist.all_gather_into_tensor(gather_buf.view(-1), y.reshape(-1).contiguous())
         return y
 
     def barrier():

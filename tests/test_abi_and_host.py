@@ -1,0 +1,104 @@
+"""CPU: the C-ABI library loads and exports every symbol include/svr2.h declares (no compute
+calls without a GPU); host-side integer logic (windows, layouts, padding, sharding)."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import dit_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(svr2lib):
+    import __graft_entry__
+    __graft_entry__.build()
+    hdr = open(os.path.join(ROOT, "include", "svr2.h")).read()
+    declared = set(re.findall(r"\b(svr2_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    lib = svr2lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/svr2.h but not exported"
+    assert set(svr2lib.SIGNATURES) | {"svr2_last_error"} == declared
+    assert lib.svr2_version() >= 100
+    assert isinstance(lib.svr2_last_error(), bytes)
+
+
+def test_product_path_has_no_oracle_or_fallback():
+    pk = os.path.join(ROOT, "comfyui-seedvr2_videoupscaler_b200")
+    for fn in os.listdir(pk):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pk, fn)).read()
+            assert "oracle" not in src.replace("oracle/", ""), f"{fn} must not import the oracle"
+            assert "scaled_dot_product_attention" not in src and "F.conv3d" not in src
+
+
+@pytest.mark.parametrize("thw,counts", [((1, 32, 32), (4, 9)), ((5, 68, 120), (75, 90)), ((3, 135, 240), (243, 300)),
+                                        ((17, 135, 240), (324, 400)), ((2, 135, 240), (162, 200))])
+def test_window_counts_match_survey(pkg, thw, counts):
+    import importlib
+    dit = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.dit")
+    for shifted, n in zip((False, True), counts):
+        boxes = dit.window_boxes(*thw, shifted)
+        assert len(boxes) == n
+        assert boxes == dit_oracle.window_boxes(*thw, shifted)
+        # every token covered exactly once
+        cover = torch.zeros(thw, dtype=torch.int32)
+        for (t0, t1, h0, h1, w0, w1) in boxes:
+            cover[t0:t1, h0:h1, w0:w1] += 1
+        assert (cover == 1).all()
+
+
+@pytest.mark.parametrize("variant", ["3b", "7b"])
+def test_layout_tables(pkg, variant):
+    import importlib
+    dit = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.dit")
+    T, Hp, Wp, l = 3, 20, 36, 58
+    L = T * Hp * Wp
+    for shifted in (False, True):
+        lay, size_rows = dit.build_layout(T, Hp, Wp, l, shifted, variant, "cpu")
+        assert lay.total == L + lay.n_win * l
+        assert lay.cu_seqlens[-1].item() == lay.total and lay.cu_seqlens[0].item() == 0
+        assert sorted(lay.out_row_map.tolist()) == list(range(lay.total))       # a permutation
+        vid_rows = lay.row_src >= 0
+        assert sorted(lay.row_src[vid_rows].tolist()) == list(range(L))
+        assert torch.equal(lay.out_row_map[vid_rows], lay.row_src[vid_rows])
+        tgt, lens, loc = dit_oracle.window_token_index(T, Hp, Wp, dit.window_boxes(T, Hp, Wp, shifted))
+        assert torch.equal(lay.row_src[vid_rows].long(), tgt)
+        if variant == "3b":
+            assert torch.equal(lay.row_rope[vid_rows].long(), loc[:, :3] + torch.tensor([l, 0, 0]))
+        fr = torch.linspace(1, 10, 10) if variant == "7b" else torch.arange(1, 22).float()
+        c, s = dit.rope_tables(fr, variant, int(lay.row_rope.max()) + 1, size_rows)
+        assert c.shape == s.shape and c.shape[0] > int(lay.row_rope.max())
+
+
+def test_rope_tables_match_oracle(pkg):
+    import importlib
+    dit = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.dit")
+    T, Hp, Wp, l = 3, 20, 36, 58
+    boxes = dit.window_boxes(T, Hp, Wp, True)
+    _, _, loc = dit_oracle.window_token_index(T, Hp, Wp, boxes)
+    for variant, freqs in (("3b", (1.0 / (10000 ** (torch.arange(0, 42, 2).float() / 42))).half()),
+                           ("7b", (torch.linspace(1.0, 128.0, 10) * torch.pi).half())):
+        lay, size_rows = dit.build_layout(T, Hp, Wp, l, True, variant, "cpu")
+        c, s = dit.rope_tables(freqs, variant, int(lay.row_rope.max()) + 1, size_rows)
+        vid_rows = lay.row_src >= 0
+        rr = lay.row_rope[vid_rows].long()
+        got = torch.cat([c[rr[:, a]].repeat_interleave(2, -1) for a in range(3)], -1)
+        if variant == "3b":
+            (cv, sv), _ = dit_oracle.rope_cos_sin_3b(freqs, loc, l)
+        else:
+            cv, sv = dit_oracle.rope_cos_sin_7b(freqs, loc)
+        assert torch.equal(got, cv)
+
+
+def test_padding_and_partition(pkg):
+    import importlib
+    pipeline = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.pipeline")
+    shard = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.shard")
+    assert [pipeline.pad_4n1(n) for n in (1, 2, 4, 5, 8, 9, 16, 17, 64)] == [1, 5, 5, 5, 9, 9, 17, 17, 65]
+    assert shard.partition_frames(64, 8) == [(8 * i, 8 * i + 8) for i in range(8)]
+    assert shard.partition_frames(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard.partition_frames(10, 3, overlap=2) == [(0, 6), (4, 9), (7, 10)]
+    assert shard.partition_frames(0, 2) == [(0, 0), (0, 0)]

@@ -1,0 +1,60 @@
+"""CPU: the oracle restatements reproduce the committed golden vectors, which were produced
+by the REFERENCE's own modules (oracle/make_golden.py).  Float tolerance 2e-4 of peak."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dit_oracle, vae_oracle
+from oracle.make_golden import DIT_CASES, VAE_CASES, dit_inputs
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", list(DIT_CASES))
+def test_dit_oracle_matches_reference_golden(pkg, name):
+    variant, over, (T, H, W), l = DIT_CASES[name]
+    cfg = dit_oracle.dit_config(variant, **over)
+    sd = {k: v.float() for k, v in pkg.weights.synth_dit_state_dict(cfg, seed=1234, dtype=torch.float16).items()}
+    vid, txt = dit_inputs(cfg, T, H, W, l)
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    assert list(g["meta"]) == [T, H, W, l]
+    taps = {}
+    out = dit_oracle.dit_forward(sd, cfg, vid, txt, T, H, W, mode="fp32", taps=taps)
+    ref = torch.from_numpy(g["out"])
+    assert (out - ref).abs().max() < 2e-4 * ref.abs().max()
+    assert (taps["emb"] - torch.from_numpy(g["emb"])).abs().max() < 1e-4
+    assert (taps["block0"][::37] - torch.from_numpy(g["block0"])).abs().max() < 2e-4 * ref.abs().max()
+
+
+@pytest.fixture(scope="module")
+def vae_sd(pkg):
+    return {k: v.float() for k, v in pkg.weights.synth_vae_state_dict(seed=4321, dtype=torch.float16).items()}
+
+
+@pytest.mark.parametrize("name", list(VAE_CASES))
+def test_vae_oracle_matches_reference_golden(vae_sd, name):
+    kind, shp = VAE_CASES[name]
+    g = torch.Generator().manual_seed(7)
+    ref = torch.from_numpy(np.load(os.path.join(GOLD, name + ".npz"))["out"])
+    if kind == "decode":
+        z = torch.randn(1, 16, *shp, generator=g)
+        out = vae_oracle.vae_decode(vae_sd, z)
+    else:
+        x = torch.rand(1, 3, *shp, generator=g) * 2 - 1
+        out = vae_oracle.vae_encode(vae_sd, x)
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max() < 2e-4 * max(ref.abs().max().item(), 1.0)
+
+
+def test_bf16_mode_is_close_to_fp32(pkg):
+    """ref_bf16 restates the reference's autocast flow; it must stay within bf16 noise of fp32."""
+    variant, over, (T, H, W), l = DIT_CASES["dit3b_tiny_t5"]
+    cfg = dit_oracle.dit_config(variant, **over)
+    sd = {k: v.float() for k, v in pkg.weights.synth_dit_state_dict(cfg, seed=1234, dtype=torch.float16).items()}
+    vid, txt = dit_inputs(cfg, T, H, W, l)
+    a = dit_oracle.dit_forward(sd, cfg, vid, txt, T, H, W, mode="fp32")
+    b = dit_oracle.dit_forward(sd, cfg, vid, txt, T, H, W, mode="ref_bf16").float()
+    psnr = 10 * torch.log10(a.abs().max() ** 2 / (a - b).pow(2).mean())
+    assert psnr > 45
