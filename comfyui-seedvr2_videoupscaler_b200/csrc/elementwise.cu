@@ -214,82 +214,153 @@ __global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ in, int ld_i
 }
 
 // ------------------------------------------------------------------ GroupNorm(32) per frame
-// stats: block handles a slab of pixels of one frame, all channels; thread owns 8 consecutive channels.
+// Deterministic three-step reduction (no floating-point atomics, so results are bit-reproducible):
+//   1. stats   : block = slab of pixels of one frame, thread = 8 fixed channels; per-block partial
+//                (sum, sumsq) per group reduced in a fixed order -> partial[f][blk][32][2] (double)
+//   2. finalize: one block per frame sums the partials in block order and emits per-channel
+//                fp32 coefficients a = rstd*gamma, b = beta - mean*a
+//   3. apply   : y = silu(bf16(a*x + b)) (+ halo duplication of frame 0)
 __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, int hw, int C,
-                                                              int pix_per_block, double* __restrict__ stats) {
-  extern __shared__ float sm[];  // [2][32]
+                                                              int pix_per_block, double* __restrict__ partial) {
+  __shared__ float sm[256][4];
   const int f = blockIdx.y;
   const int cvec = C / 8;               // vectors per pixel
   const int cpg = C / 32;               // channels per group (4, 8, 16)
-  if (threadIdx.x < 64) sm[threadIdx.x] = 0.f;
-  __syncthreads();
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   const long long p1 = min((long long)hw, p0 + pix_per_block);
   const __nv_bfloat16* xf = x + (long long)f * hw * C;
-  // thread -> fixed channel vector (tid % cvec), strided over pixels
-  const int cv = threadIdx.x % cvec, pl = threadIdx.x / cvec, pstride = blockDim.x / cvec;
-  float s[2] = {0.f, 0.f}, ss[2] = {0.f, 0.f};  // cpg==4: a vector spans 2 groups
-  for (long long p = p0 + pl; p < p1; p += pstride) {
-    float v[8];
-    unpack8(*reinterpret_cast<const uint4*>(xf + p * C + cv * 8), v);
-    if (cpg == 4) {
+  const int cv = threadIdx.x % cvec, pl = threadIdx.x / cvec, pstride = 256 / cvec;
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;   // (s0,q0): channels 0-3 of the vector, (s1,q1): 4-7
+  long long p = p0 + pl;
+  for (; p + 3LL * pstride < p1; p += 4LL * pstride) {
+    uint4 r[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { s[0] += v[e]; ss[0] += v[e] * v[e]; s[1] += v[4 + e]; ss[1] += v[4 + e] * v[4 + e]; }
-    } else {
+    for (int u = 0; u < 4; ++u) r[u] = *reinterpret_cast<const uint4*>(xf + (p + (long long)u * pstride) * C + cv * 8);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { s[0] += v[e]; ss[0] += v[e] * v[e]; }
+    for (int u = 0; u < 4; ++u) {
+      float v[8];
+      unpack8(r[u], v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s0 += v[e]; q0 += v[e] * v[e]; s1 += v[4 + e]; q1 += v[4 + e] * v[4 + e]; }
     }
   }
-  if (cpg == 4) {
-    atomicAdd(&sm[cv * 2], s[0]); atomicAdd(&sm[32 + cv * 2], ss[0]);
-    atomicAdd(&sm[cv * 2 + 1], s[1]); atomicAdd(&sm[32 + cv * 2 + 1], ss[1]);
-  } else {
-    const int g = (cv * 8) / cpg;
-    atomicAdd(&sm[g], s[0]); atomicAdd(&sm[32 + g], ss[0]);
+  for (; p < p1; p += pstride) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(xf + p * C + cv * 8), v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { s0 += v[e]; q0 += v[e] * v[e]; s1 += v[4 + e]; q1 += v[4 + e] * v[4 + e]; }
+  }
+  sm[threadIdx.x][0] = s0; sm[threadIdx.x][1] = q0; sm[threadIdx.x][2] = s1; sm[threadIdx.x][3] = q1;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x;
+    double ds = 0.0, dq = 0.0;
+    if (cpg == 4) {               // group g = half (g&1) of vector g>>1
+      const int v = g >> 1, h = (g & 1) * 2;
+      for (int l = 0; l < pstride; ++l) { ds += sm[l * cvec + v][h]; dq += sm[l * cvec + v][h + 1]; }
+    } else {                      // group g = vectors [g*cpg/8, (g+1)*cpg/8)
+      const int nv = cpg / 8;
+      for (int l = 0; l < pstride; ++l)
+        for (int v = g * nv; v < (g + 1) * nv; ++v) {
+          ds += (double)sm[l * cvec + v][0] + (double)sm[l * cvec + v][2];
+          dq += (double)sm[l * cvec + v][1] + (double)sm[l * cvec + v][3];
+        }
+    }
+    double* dst = partial + (((long long)f * gridDim.x + blockIdx.x) * 32 + g) * 2;
+    dst[0] = ds;
+    dst[1] = dq;
+  }
+}
+
+// grid = frames, block = 256: coef[f][c] = (a, b)
+__global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const double* __restrict__ partial, int nblk, int hw,
+                                                                 int C, const __nv_bfloat16* __restrict__ gamma,
+                                                                 const __nv_bfloat16* __restrict__ beta, float eps,
+                                                                 float2* __restrict__ coef) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int f = blockIdx.x, cpg = C / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp w reduces groups w, w+8, ... : lanes stride over blocks, then a fixed-order shuffle tree
+  for (int g = warp; g < 32; g += 8) {
+    double ds = 0.0, dq = 0.0;
+    for (int b = lane; b < nblk; b += 32) {
+      const double* src = partial + (((long long)f * nblk + b) * 32 + g) * 2;
+      ds += src[0];
+      dq += src[1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ds += __shfl_xor_sync(0xffffffffu, ds, o);
+      dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    }
+    if (lane == 0) {
+      const double n = (double)hw * cpg;
+      const double mean = ds / n, var = dq / n - mean * mean;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = rsqrtf(fmaxf((float)var, 0.f) + eps);
+    }
   }
   __syncthreads();
-  if (threadIdx.x < 64) {
-    const int g = threadIdx.x & 31, which = threadIdx.x >> 5;
-    atomicAdd(&stats[((long long)f * 32 + g) * 2 + which], (double)sm[threadIdx.x]);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c / cpg;
+    const float a = s_rstd[g] * __bfloat162float(gamma[c]);
+    coef[(long long)f * C + c] = make_float2(a, __bfloat162float(beta[c]) - s_mean[g] * a);
   }
 }
 
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x,
-                                                              __nv_bfloat16* __restrict__ y, int hw, int C,
-                                                              const __nv_bfloat16* __restrict__ gamma,
-                                                              const __nv_bfloat16* __restrict__ beta, float eps,
-                                                              int silu, int out_t_pad, int out_dup_head,
-                                                              const double* __restrict__ stats) {
+                                                              __nv_bfloat16* __restrict__ y, int hw, int C, int silu,
+                                                              int out_t_pad, int out_dup_head,
+                                                              const float2* __restrict__ coef) {
   const int f = blockIdx.y;
-  const int cvec = C / 8, cpg = C / 32;
+  const int cvec = C / 8;
   const long long nvec = (long long)hw * cvec;
-  const double n = (double)hw * cpg;
   const __nv_bfloat16* xf = x + (long long)f * hw * C;
   __nv_bfloat16* yf = y + (long long)(f + out_t_pad) * hw * C;
-  // 256 % cvec == 0 and the grid stride is a multiple of 256, so a thread always owns the same 8 channels
+  // 256 % cvec == 0 and every stride below is a multiple of 256: a thread always owns the same 8 channels
   const int cv = threadIdx.x % cvec;
   float ca[8], cb[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int ch = cv * 8 + e, g = ch / cpg;
-    const double mean_d = stats[((long long)f * 32 + g) * 2] / n;
-    const double var_d = stats[((long long)f * 32 + g) * 2 + 1] / n - mean_d * mean_d;
-    const float rstd = rsqrtf(fmaxf((float)var_d, 0.f) + eps);
-    ca[e] = rstd * __bfloat162float(gamma[ch]);
-    cb[e] = __bfloat162float(beta[ch]) - (float)mean_d * ca[e];
+    const float2 t = coef[(long long)f * C + cv * 8 + e];
+    ca[e] = t.x;
+    cb[e] = t.y;
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
+  const bool dup = out_dup_head && f == 0;
+  const long long stride = (long long)gridDim.x * 256;
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = reinterpret_cast<const uint4*>(xf)[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8], o[8];
+      unpack8(r[u], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float t = bf16_round(v[e] * ca[e] + cb[e]);   // F.group_norm output is bf16
+        o[e] = silu ? silu_f(t) : t;
+      }
+      const uint4 pk = pack8(o);
+      reinterpret_cast<uint4*>(yf)[i + u * stride] = pk;
+      if (dup) {
+        reinterpret_cast<uint4*>(yf - (long long)hw * C)[i + u * stride] = pk;
+        reinterpret_cast<uint4*>(yf - 2LL * hw * C)[i + u * stride] = pk;
+      }
+    }
+  }
+  for (; i < nvec; i += stride) {
     float v[8], o[8];
     unpack8(reinterpret_cast<const uint4*>(xf)[i], v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float t = bf16_round(v[e] * ca[e] + cb[e]);   // F.group_norm output is bf16
+      const float t = bf16_round(v[e] * ca[e] + cb[e]);
       o[e] = silu ? silu_f(t) : t;
     }
     const uint4 pk = pack8(o);
     reinterpret_cast<uint4*>(yf)[i] = pk;
-    if (out_dup_head && f == 0) {
+    if (dup) {
       reinterpret_cast<uint4*>(yf - (long long)hw * C)[i] = pk;
       reinterpret_cast<uint4*>(yf - 2LL * hw * C)[i] = pk;
     }
@@ -451,26 +522,42 @@ extern "C" int svr2_unpatchify_bf16(const void* in, int ld_in, void* out, int T,
 
 extern "C" int svr2_groupnorm_bf16(const void* x, void* y, int frames, int hw, int C, const void* gamma,
                                    const void* beta, float eps, int silu, int out_t_pad, int out_dup_head,
-                                   double* stats, void* stream) {
-  if (C % 32 || (C / 32 != 4 && C / 32 != 8 && C / 32 != 16) || 256 % (C / 8))
+                                   double* scratch, int64_t scratch_bytes, void* stream) {
+  if (C % 32 || (C / 32 != 4 && C / 32 != 8 && C / 32 != 16))
     return set_error(SVR2_ERR_ARG, "groupnorm: C must be 128, 256 or 512");
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 64 * frames, s);
-  if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
-  // ~4 waves of blocks per frame set
-  int blocks_x = (int)((hw + 2047) / 2048);
+  int blocks_x = (int)((hw + 4095) / 4096);
   if (blocks_x < 1) blocks_x = 1;
   const int ppb = (hw + blocks_x - 1) / blocks_x;
-  groupnorm_stats_kernel<<<dim3(blocks_x, frames), 256, 64 * sizeof(float), s>>>((const __nv_bfloat16*)x, hw, C, ppb, stats);
+  const size_t partial_bytes = sizeof(double) * 64 * (size_t)blocks_x * frames;
+  const size_t coef_bytes = sizeof(float2) * (size_t)frames * C;
+  if ((size_t)scratch_bytes < partial_bytes + coef_bytes) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "groupnorm: scratch too small (%lld < %zu bytes)", (long long)scratch_bytes,
+             partial_bytes + coef_bytes);
+    return set_error(SVR2_ERR_ARG, msg);
+  }
+  float2* coef = reinterpret_cast<float2*>(reinterpret_cast<char*>(scratch) + partial_bytes);
+  groupnorm_stats_kernel<<<dim3(blocks_x, frames), 256, 0, s>>>((const __nv_bfloat16*)x, hw, C, ppb, scratch);
   int rc = check_launch("groupnorm_stats");
   if (rc) return rc;
+  groupnorm_finalize_kernel<<<frames, 256, 0, s>>>(scratch, blocks_x, hw, C, (const __nv_bfloat16*)gamma,
+                                                   (const __nv_bfloat16*)beta, eps, coef);
+  rc = check_launch("groupnorm_finalize");
+  if (rc) return rc;
   const long long nvec = (long long)hw * C / 8;
-  int bx = (int)((nvec + 256 * 4 - 1) / (256 * 4));
+  int bx = (int)((nvec + 256 * 8 - 1) / (256 * 8));
   if (bx < 1) bx = 1;
-  groupnorm_apply_kernel<<<dim3(bx, frames), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, C,
-                                                          (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps,
-                                                          silu, out_t_pad, out_dup_head, stats);
+  groupnorm_apply_kernel<<<dim3(bx, frames), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, C, silu,
+                                                          out_t_pad, out_dup_head, coef);
   return check_launch("groupnorm_apply");
+}
+
+/* bytes of scratch svr2_groupnorm_bf16 needs for (frames, hw, C) */
+extern "C" int64_t svr2_groupnorm_scratch_bytes(int frames, int hw, int C) {
+  long long blocks_x = (hw + 4095) / 4096;
+  if (blocks_x < 1) blocks_x = 1;
+  return (int64_t)(sizeof(double) * 64 * blocks_x * frames + sizeof(float2) * (long long)frames * C);
 }
 
 extern "C" int svr2_softmax_rows_bf16(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols,

@@ -7,11 +7,12 @@
 // by 4-D/5-D TMA with out-of-bounds zero fill = spatial zero padding; the causal
 // temporal halo is two real frames stored in front of every activation tensor).
 //
-// Roles (256 threads, 1 CTA / SM, grid = #SMs, static tile schedule):
+// Roles (384 threads, 1 CTA / SM, grid = #SMs, static tile schedule):
 //   warp 0 : TMA producer   (kStages-deep smem ring, 128B-swizzled K-major tiles)
 //   warp 1 : MMA issuer     (one elected lane, tcgen05.mma cta_group::1, M=128,N=BLOCK_N,K=16)
 //   warp 2 : TMEM allocator (2 accumulator stages so the epilogue overlaps the next tile)
-//   warps 4-7 : epilogue    (tcgen05.ld 32x32b -> registers -> fused math -> 16-byte global stores)
+//   warps 4-11: epilogue    (tcgen05.ld 32x32b -> registers -> fused math -> swizzled smem slab ->
+//                            row-contiguous 16-byte global stores; two warps per TMEM lane quadrant)
 //
 // Reference semantics replaced: nn.Linear (dit_3b/mmattn.py:56-59,173,269; mlp.py:56-61;
 // patch_v1.py:37,62), InflatedCausalConv3d (causal_inflation_lib.py:213-305), Upsample3D's
@@ -32,7 +33,7 @@ namespace svr2 {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 384;   // 4 control warps + 8 epilogue warps
 
 struct GemmParams {
   int M, N, K;
@@ -79,12 +80,65 @@ struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kStagingBytes = 8 * 4096;            // epilogue: 8 warps x (32 rows x 128 B)
+  static constexpr int kBudget = 232448 - kStagingBytes - 256 - 1024;   // 227 KB max dynamic smem
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static constexpr int kStagingOffset = kStages * kStageBytes;
+  static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
+enum : int { KIND_BF16 = 0, KIND_SWIGLU = 1, KIND_F32 = 2 };
+
+// One tile's output row of a thread: destination offset (elements), validity, halo duplication.
+struct RowDest {
+  long long off;
+  int valid;
+  int dup;
+};
+
 template <int BLOCK_N>
+__device__ __forceinline__ RowDest row_dest(const GemmParams& p, int m_blk, int n_blk, int row, int n_cols) {
+  RowDest d;
+  d.dup = 0;
+  if (p.epi & EPI_SHUFFLE) {
+    const int m = m_blk * BLOCK_M + row;
+    d.valid = m < p.M;
+    const int hw = p.shuf_H * p.shuf_W;
+    const int f = m / hw, rr = m - f * hw, h = rr / p.shuf_W, w = rr - h * p.shuf_W;
+    // channel n = ((x*2 + y)*Z + z)*C + c ; a BLOCK_N tile never straddles a (x,y,z) group
+    const int grp = (n_blk * BLOCK_N) / p.shuf_c;
+    const int z = grp % p.shuf_z, y = (grp / p.shuf_z) & 1, x = grp / (p.shuf_z * 2);
+    int t_out = f * p.shuf_z + z;
+    if (p.shuf_drop) {
+      // remove_head (causal_inflation_lib.py:412-419): keep (f=0,z=0), drop (f=0,z=1)
+      if (f == 0 && z == 1) d.valid = 0;
+      if (f > 0) t_out -= 1;
+    }
+    const int Wo = p.shuf_W * 2;
+    const long long pix = (long long)(2 * h + x) * Wo + (2 * w + y);
+    d.off = (long long)(t_out + p.out_t_pad) * p.out_frame_stride + pix * p.ldc + ((n_blk * BLOCK_N) % p.shuf_c);
+    d.dup = (p.out_dup_head && t_out == 0 && d.valid) ? 1 : 0;
+  } else if (p.a_mode == 0) {
+    const int m = m_blk * BLOCK_M + row;
+    d.valid = m < p.M;
+    d.off = (long long)m * p.ldc + (long long)n_blk * n_cols;
+  } else {
+    const int per_frame = p.tiles_w * p.tiles_h;
+    const int t_o = m_blk / per_frame, r = m_blk - t_o * per_frame;
+    const int th = r / p.tiles_w, tw = r - th * p.tiles_w;
+    const int rh = row / p.bw;
+    const int h = th * p.bh + rh;
+    const int w = tw * p.bw + (row - rh * p.bw);
+    d.valid = (h < p.H_out) && (w < p.W_out);
+    d.off = (long long)(t_o + p.out_t_pad) * p.out_frame_stride + ((long long)h * p.W_out + w) * p.ldc +
+            (long long)n_blk * BLOCK_N;
+    d.dup = (p.out_dup_head && t_o == 0 && d.valid) ? 1 : 0;
+  }
+  return d;
+}
+
+template <int BLOCK_N, int KIND>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
@@ -115,7 +169,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 256);
     }
     fence_barrier_init();
   }
@@ -126,43 +180,70 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_n_tiles = p.num_n_tiles;
 
   if (warp == 0) {
     // ========================= TMA producer =========================
+    // A single thread feeds the ring; the per-k-block path is kept free of divisions and
+    // parameter reloads (it was the bottleneck of the first version: ~680 cycles per k-block).
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
-        int t_o = 0, h0 = 0, w0 = 0;
-        if (p.a_mode != 0) {
-          const int per_frame = p.tiles_w * p.tiles_h;
-          t_o = m_blk / per_frame;
-          const int r = m_blk % per_frame;
-          h0 = (r / p.tiles_w) * p.bh;
-          w0 = (r % p.tiles_w) * p.bw;
+      const int a_mode = p.a_mode;
+      const int nkb = p.num_k_blocks;
+      auto acquire = [&](uint8_t*& sa, uint64_t*& fb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        sa = smem + stage * L::kStageBytes;
+        fb = &full_bar[stage];
+        mbar_expect_tx(fb, L::kStageBytes);
+      };
+      auto advance = [&]() {
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      };
+      if (a_mode == 0) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int m_blk = tile / num_n_tiles, n_blk = tile - m_blk * num_n_tiles;
+          const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+          for (int kb = 0; kb < nkb; ++kb) {
+            uint8_t* sa; uint64_t* fb;
+            acquire(sa, fb);
+            tma_load_2d(sa, &tmap_a, fb, kb * BLOCK_K, m0);
+            tma_load_2d(sa + L::kABytes, &tmap_b, fb, kb * BLOCK_K, n0);
+            advance();
+          }
         }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-          if (p.a_mode == 0) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          } else {
-            const int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
-            const int kw_ = tap % p.taps_w, kh_ = (tap / p.taps_w) % p.taps_h, kt_ = tap / (p.taps_w * p.taps_h);
-            const int t_in = t_o * p.stride_t + kt_;
-            if (p.a_mode == 1) {
-              tma_load_4d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, w0 + kw_ - p.pad_w, h0 + kh_ - p.pad_h, t_in);
-            } else {
-              // pair view (2C, W/2, 2, H/2, T): input pixel 2*o + k -> pair o + k/2, phase k%2
-              tma_load_5d(sa, &tmap_a, &full_bar[stage], (kw_ & 1) * p.cin + cb * BLOCK_K, w0 + (kw_ >> 1),
-                          kh_ & 1, h0 + (kh_ >> 1), t_in);
+      } else {
+        const int per_frame = p.tiles_w * p.tiles_h, tiles_w = p.tiles_w;
+        const int bw = p.bw, bh = p.bh, pad_h = p.pad_h, pad_w = p.pad_w, stride_t = p.stride_t;
+        const int taps_t = p.taps_t, taps_h = p.taps_h, taps_w = p.taps_w, cin_blocks = p.cin_blocks, cin = p.cin;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int m_blk = tile / num_n_tiles, n_blk = tile - m_blk * num_n_tiles;
+          const int t_o = m_blk / per_frame, r = m_blk - t_o * per_frame;
+          const int th = r / tiles_w;
+          const int h0 = th * bh, w0 = (r - th * tiles_w) * bw;
+          const int n0 = n_blk * BLOCK_N;
+          int kcol = 0;
+          for (int kt_ = 0; kt_ < taps_t; ++kt_) {
+            const int t_in = t_o * stride_t + kt_;
+            for (int kh_ = 0; kh_ < taps_h; ++kh_) {
+              for (int kw_ = 0; kw_ < taps_w; ++kw_) {
+                for (int cb = 0; cb < cin_blocks; ++cb) {
+                  uint8_t* sa; uint64_t* fb;
+                  acquire(sa, fb);
+                  if (a_mode == 1) {
+                    tma_load_4d(sa, &tmap_a, fb, cb * BLOCK_K, w0 + kw_ - pad_w, h0 + kh_ - pad_h, t_in);
+                  } else {
+                    // pair view (2C, W/2, 2, H/2, T): input pixel 2*o + k -> pair o + k/2, phase k%2
+                    tma_load_5d(sa, &tmap_a, fb, (kw_ & 1) * cin + cb * BLOCK_K, w0 + (kw_ >> 1), kh_ & 1,
+                                h0 + (kh_ >> 1), t_in);
+                  }
+                  tma_load_2d(sa + L::kABytes, &tmap_b, fb, kcol, n0);
+                  kcol += BLOCK_K;
+                  advance();
+                }
+              }
             }
           }
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -170,6 +251,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ========================= MMA issuer =========================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      const int nkb = p.num_k_blocks;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -178,13 +260,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t b_addr = a_addr + L::kABytes;
           const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
-          const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(a_addr + L::kABytes);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in the >>4 address field
@@ -198,162 +279,182 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ========================= epilogue =========================
+    // ========================= epilogue (8 warps) =========================
+    // Two warps per TMEM lane quadrant (warp % 4), each owning half of the tile's columns, so every
+    // SM sub-partition has two epilogue warps to hide instruction latency.
+    // Phase 1: a thread owns one accumulator row: tcgen05.ld 32 columns at a time, fused math, result
+    //          (bf16 or fp32) into a per-warp XOR-swizzled staging slab (32 rows x 128 B).
+    // Phase 2: the warp re-reads the slab row-major so that every global load/store instruction covers
+    //          contiguous 128-byte row segments (16 B per lane); residual loads are issued in batches
+    //          before use, then add + store (+ halo copies).
+    constexpr int N_COLS = KIND == KIND_SWIGLU ? ACC_STRIDE / 2 : ACC_STRIDE;   // output columns per tile
+    constexpr int COLS_W = N_COLS >= 64 ? N_COLS / 2 : N_COLS;                 // columns per epilogue warp
+    constexpr int PH_COLS = KIND == KIND_F32 ? 32 : (COLS_W < 64 ? COLS_W : 64);
+    constexpr int CPR = KIND == KIND_F32 ? PH_COLS / 4 : PH_COLS / 8;    // 16-byte chunks per staged row
+    constexpr int ROWS_PER_IT = 32 / CPR;
+    constexpr int N_IT = 32 / ROWS_PER_IT;                                // warp-wide accesses per phase
+    constexpr int kBatch = N_IT < 4 ? N_IT : 4;
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;     // which half of the columns
     const int row = q * 32 + lane;        // tile row owned by this thread
+    const bool active = (N_COLS >= 64) || (half == 0);
+    const int col_lo = (N_COLS >= 64) ? half * COLS_W : 0;
+    uint8_t* slab = smem + L::kStagingOffset + (warp - 4) * 4096;
+    const int epi = p.epi;
+    const int n_lim = KIND == KIND_SWIGLU ? p.N / 2 : p.N;
+    const __nv_bfloat16* __restrict__ bias = p.bias;
+    const float* __restrict__ gate = p.gate;
+    const __nv_bfloat16* __restrict__ resid = p.residual;
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr int N_OUT = ACC_STRIDE;      // accumulator columns read per tile
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
-      // ---- where does this row go? ----
-      bool valid;
-      long long off0 = 0, off_dup1 = -1, off_dup2 = -1;
-      if (p.epi & EPI_SHUFFLE) {
-        const int m = m_blk * BLOCK_M + row;
-        valid = m < p.M;
-        const int hw = p.shuf_H * p.shuf_W;
-        const int f = m / hw, rr = m % hw, h = rr / p.shuf_W, w = rr % p.shuf_W;
-        // channel n = ((x*2 + y)*Z + z)*C + c ; a BLOCK_N tile never straddles a (x,y,z) group
-        const int grp = (n_blk * BLOCK_N) / p.shuf_c;
-        const int z = grp % p.shuf_z, y = (grp / p.shuf_z) & 1, x = grp / (p.shuf_z * 2);
-        int t_out = f * p.shuf_z + z;
-        if (p.shuf_drop) {
-          // remove_head (causal_inflation_lib.py:412-419): keep (f=0,z=0), drop (f=0,z=1)
-          if (f == 0 && z == 1) valid = false;
-          if (f > 0) t_out -= 1;
-        }
-        const int Ho = p.shuf_H * 2, Wo = p.shuf_W * 2;
-        const long long pix = (long long)(2 * h + x) * Wo + (2 * w + y);
-        off0 = (long long)(t_out + p.out_t_pad) * p.out_frame_stride + pix * p.ldc +
-               ((n_blk * BLOCK_N) % p.shuf_c);
-        if (p.out_dup_head && t_out == 0) {
-          off_dup1 = off0 - p.out_frame_stride;
-          off_dup2 = off0 - 2 * p.out_frame_stride;
-        }
-        (void)Ho;
-      } else if (p.a_mode == 0) {
-        const int m = m_blk * BLOCK_M + row;
-        valid = m < p.M;
-        off0 = (long long)m * p.ldc + (long long)n_blk * ((p.epi & EPI_SWIGLU) ? BLOCK_N / 2 : BLOCK_N);
-      } else {
-        const int per_frame = p.tiles_w * p.tiles_h;
-        const int t_o = m_blk / per_frame, r = m_blk % per_frame;
-        const int h = (r / p.tiles_w) * p.bh + row / p.bw;
-        const int w = (r % p.tiles_w) * p.bw + row % p.bw;
-        valid = (h < p.H_out) && (w < p.W_out);
-        off0 = (long long)(t_o + p.out_t_pad) * p.out_frame_stride + ((long long)h * p.W_out + w) * p.ldc +
-               (long long)n_blk * BLOCK_N;
-        if (p.out_dup_head && t_o == 0) {
-          off_dup1 = off0 - p.out_frame_stride;
-          off_dup2 = off0 - 2 * p.out_frame_stride;
-        }
-      }
+      const int m_blk = tile / num_n_tiles, n_blk = tile - m_blk * num_n_tiles;
+      const RowDest dst = row_dest<BLOCK_N>(p, m_blk, n_blk, row, N_COLS);
+      const int n_base = n_blk * (KIND == KIND_SWIGLU ? BLOCK_N / 2 : BLOCK_N);   // first output column
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_STRIDE;
-      const int n_base = n_blk * BLOCK_N;
 
-      if (p.epi & EPI_SWIGLU) {
-        constexpr int HALF = N_OUT / 2;
-#pragma unroll 1
-        for (int c0 = 0; c0 < HALF; c0 += 32) {
-          uint32_t g[32], u[32];
-          tmem_ld32(t_addr + c0, g);
-          tmem_ld32(t_addr + HALF + c0, u);
-          tmem_ld_wait();
-          if (valid) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off0 + c0;
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float g0 = bf16_round(__uint_as_float(g[j])), g1 = bf16_round(__uint_as_float(g[j + 1]));
-              float u0 = bf16_round(__uint_as_float(u[j])), u1 = bf16_round(__uint_as_float(u[j + 1]));
-              pk[j / 2] = pack_bf16x2(bf16_round(silu_f(g0)) * u0, bf16_round(silu_f(g1)) * u1);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              reinterpret_cast<uint4*>(o)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
-        }
-      } else if (p.epi & EPI_F32) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < N_OUT; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_addr + c0, v);
-          tmem_ld_wait();
-          if (valid && n_base + c0 < p.N) {
-            float* o = reinterpret_cast<float*>(p.out) + off0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (n_base + c0 + j < p.N)
-                *reinterpret_cast<float4*>(o + j) =
-                    make_float4(__uint_as_float(v[j]) * p.out_scale, __uint_as_float(v[j + 1]) * p.out_scale,
-                                __uint_as_float(v[j + 2]) * p.out_scale, __uint_as_float(v[j + 3]) * p.out_scale);
-            }
-          }
-        }
+      if (!active) {
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
       } else {
 #pragma unroll 1
-        for (int c0 = 0; c0 < N_OUT; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_addr + c0, v);
-          tmem_ld_wait();
-          if (valid && n_base + c0 < p.N) {
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        for (int ph0 = col_lo; ph0 < col_lo + COLS_W; ph0 += PH_COLS) {
+          // ---------------- phase 1 ----------------
+#pragma unroll 1
+          for (int c0 = ph0; c0 < ph0 + PH_COLS; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(t_addr + c0, v);
             const int n0 = n_base + c0;
-            if (p.epi & EPI_BIAS) {
+            if constexpr (KIND == KIND_SWIGLU) {
+              uint32_t u[32];
+              tmem_ld32(t_addr + ACC_STRIDE / 2 + c0, u);
+              tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += (n0 + j < p.N) ? __bfloat162float(p.bias[n0 + j]) : 0.f;
-            }
+              for (int j = 0; j < 32; ++j) {
+                const float g0 = bf16_rne(__uint_as_float(v[j])), u0 = bf16_rne(__uint_as_float(u[j]));
+                v[j] = __float_as_uint(bf16_rne(bf16_rne(silu_fast(g0)) * u0));
+              }
+            } else if constexpr (KIND == KIND_F32) {
+              tmem_ld_wait();
+              const float sc = p.out_scale;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
-            if (p.epi & EPI_GELU) {
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * sc);
+            } else {
+              tmem_ld_wait();
+              // per-column operands, 8 columns at a time (N % 8 == 0: a group is all-valid or all-OOB)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = bf16_round(gelu_tanh_f(f[j]));
-            }
-            if (p.epi & EPI_SILU) {
+              for (int g8 = 0; g8 < 4; ++g8) {
+                const bool ok = (n0 + 8 * g8) < p.N;
+                if (epi & EPI_BIAS) {
+                  const uint4 bv = ok ? *reinterpret_cast<const uint4*>(bias + n0 + 8 * g8) : make_uint4(0, 0, 0, 0);
+                  const uint32_t bw_[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = bf16_round(silu_f(f[j]));
-            }
-            if (p.epi & EPI_GATE) {
+                  for (int e = 0; e < 4; ++e) {
+                    v[8 * g8 + 2 * e] = __float_as_uint(__uint_as_float(v[8 * g8 + 2 * e]) + __uint_as_float(bw_[e] << 16));
+                    v[8 * g8 + 2 * e + 1] =
+                        __float_as_uint(__uint_as_float(v[8 * g8 + 2 * e + 1]) + __uint_as_float(bw_[e] & 0xffff0000u));
+                  }
+                }
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j] * ((n0 + j < p.N) ? p.gate[n0 + j] : 0.f));
-            }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off0 + c0;
-            if (p.epi & EPI_RESIDUAL) {
-              const __nv_bfloat16* rs = p.residual + off0 + c0;
+                for (int e = 0; e < 8; ++e) v[8 * g8 + e] = __float_as_uint(bf16_rne(__uint_as_float(v[8 * g8 + e])));
+                if (epi & EPI_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (n0 + j < p.N) {
-                  uint4 rv = *reinterpret_cast<const uint4*>(rs + j);
-                  const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(&rv);
+                  for (int e = 0; e < 8; ++e)
+                    v[8 * g8 + e] = __float_as_uint(bf16_rne(gelu_tanh_fast(__uint_as_float(v[8 * g8 + e]))));
+                }
+                if (epi & EPI_SILU) {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) f[j + e] += __bfloat162float(rb[e]);
+                  for (int e = 0; e < 8; ++e)
+                    v[8 * g8 + e] = __float_as_uint(bf16_rne(silu_fast(__uint_as_float(v[8 * g8 + e]))));
+                }
+                if (epi & EPI_GATE) {
+                  const float4 ga = ok ? *reinterpret_cast<const float4*>(gate + n0 + 8 * g8) : make_float4(0, 0, 0, 0);
+                  const float4 gb = ok ? *reinterpret_cast<const float4*>(gate + n0 + 8 * g8 + 4) : make_float4(0, 0, 0, 0);
+                  const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    v[8 * g8 + e] = __float_as_uint(bf16_rne(__uint_as_float(v[8 * g8 + e]) * gg[e]));
                 }
               }
             }
+            // stage: chunk index within the phase row, XOR-swizzled by the row
+            if constexpr (KIND == KIND_F32) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (n0 + j < p.N) {
-                uint4 pk = make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
-                                      pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
-                *reinterpret_cast<uint4*>(o + j) = pk;
-                if (off_dup1 >= 0) {
-                  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
-                  *reinterpret_cast<uint4*>(ob + off_dup1 + c0 + j) = pk;
-                  *reinterpret_cast<uint4*>(ob + off_dup2 + c0 + j) = pk;
+              for (int j = 0; j < 8; ++j) {
+                const int ch = j ^ (lane & (CPR - 1));
+                *reinterpret_cast<uint4*>(slab + lane * 128 + ch * 16) =
+                    make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+            } else {
+              // values are already bf16-representable: packing is a byte permute (no conversion)
+              const int cbase = (c0 - ph0) / 8;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int ch = (cbase + j) ^ (lane & (CPR - 1));
+                *reinterpret_cast<uint4*>(slab + lane * 128 + ch * 16) =
+                    make_uint4(__byte_perm(v[8 * j], v[8 * j + 1], 0x7632), __byte_perm(v[8 * j + 2], v[8 * j + 3], 0x7632),
+                               __byte_perm(v[8 * j + 4], v[8 * j + 5], 0x7632), __byte_perm(v[8 * j + 6], v[8 * j + 7], 0x7632));
+              }
+            }
+          }
+          if (ph0 + PH_COLS >= col_lo + COLS_W) {   // all TMEM reads of this warp are done for this tile
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+          __syncwarp();
+          // ---------------- phase 2 ----------------
+          const int ch = lane % CPR, rsub = lane / CPR;
+          const int col = ph0 + (KIND == KIND_F32 ? ch * 4 : ch * 8);
+          const bool col_ok = (n_base + col) < n_lim;
+#pragma unroll 1
+          for (int b0 = 0; b0 < N_IT; b0 += kBatch) {
+            long long off[kBatch];
+            int flags[kBatch];
+            uint4 rv[kBatch];
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) {
+              const int r = (b0 + i) * ROWS_PER_IT + rsub;
+              off[i] = __shfl_sync(0xffffffffu, dst.off, r);
+              const int f = __shfl_sync(0xffffffffu, dst.valid | (dst.dup << 1), r);
+              flags[i] = col_ok ? f : 0;
+              if constexpr (KIND == KIND_BF16) {
+                if ((epi & EPI_RESIDUAL) && (flags[i] & 1)) rv[i] = *reinterpret_cast<const uint4*>(resid + off[i] + col);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) {
+              if (!(flags[i] & 1)) continue;
+              const int r = (b0 + i) * ROWS_PER_IT + rsub;
+              uint4 d = *reinterpret_cast<const uint4*>(slab + r * 128 + ((ch ^ (r & (CPR - 1))) << 4));
+              if constexpr (KIND == KIND_F32) {
+                *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + off[i] + col) = d;
+              } else {
+                __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
+                if constexpr (KIND == KIND_BF16) {
+                  if (epi & EPI_RESIDUAL) {
+                    const uint32_t dw[4] = {d.x, d.y, d.z, d.w}, rw[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                      o[e] = pack_bf16x2(__uint_as_float(dw[e] << 16) + __uint_as_float(rw[e] << 16),
+                                         __uint_as_float(dw[e] & 0xffff0000u) + __uint_as_float(rw[e] & 0xffff0000u));
+                    d = make_uint4(o[0], o[1], o[2], o[3]);
+                  }
+                }
+                *reinterpret_cast<uint4*>(ob + off[i] + col) = d;
+                if (flags[i] & 2) {
+                  *reinterpret_cast<uint4*>(ob + off[i] - p.out_frame_stride + col) = d;
+                  *reinterpret_cast<uint4*>(ob + off[i] - 2 * p.out_frame_stride + col) = d;
                 }
               }
             }
           }
+          __syncwarp();
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -422,20 +523,20 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int KIND>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, KIND>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
     configured = true;
   }
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid <= 0) return SVR2_OK;
-  gemm_tcgen05_kernel<BLOCK_N><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
+  gemm_tcgen05_kernel<BLOCK_N, KIND><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
   return SVR2_OK;
@@ -443,12 +544,25 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 
 static int dispatch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                          cudaStream_t s) {
+  if (p.epi & EPI_SWIGLU) {
+    if (block_n == 256) return launch_gemm<256, KIND_SWIGLU>(ta, tb, p, s);
+    return set_error(SVR2_ERR_ARG, "SwiGLU epilogue needs BLOCK_N = 256");
+  }
+  if (p.epi & EPI_F32) {
+    switch (block_n) {
+      case 256: return launch_gemm<256, KIND_F32>(ta, tb, p, s);
+      case 128: return launch_gemm<128, KIND_F32>(ta, tb, p, s);
+      case 64: return launch_gemm<64, KIND_F32>(ta, tb, p, s);
+      case 32: return launch_gemm<32, KIND_F32>(ta, tb, p, s);
+      case 16: return launch_gemm<16, KIND_F32>(ta, tb, p, s);
+    }
+  }
   switch (block_n) {
-    case 256: return launch_gemm<256>(ta, tb, p, s);
-    case 128: return launch_gemm<128>(ta, tb, p, s);
-    case 64: return launch_gemm<64>(ta, tb, p, s);
-    case 32: return launch_gemm<32>(ta, tb, p, s);
-    case 16: return launch_gemm<16>(ta, tb, p, s);
+    case 256: return launch_gemm<256, KIND_BF16>(ta, tb, p, s);
+    case 128: return launch_gemm<128, KIND_BF16>(ta, tb, p, s);
+    case 64: return launch_gemm<64, KIND_BF16>(ta, tb, p, s);
+    case 32: return launch_gemm<32, KIND_BF16>(ta, tb, p, s);
+    case 16: return launch_gemm<16, KIND_BF16>(ta, tb, p, s);
   }
   return set_error(SVR2_ERR_ARG, "unsupported BLOCK_N");
 }

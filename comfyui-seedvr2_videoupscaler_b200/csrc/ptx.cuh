@@ -195,6 +195,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// round-to-nearest-even to bf16 precision with integer ops (no F2F conversion; NaN not preserved)
+__device__ __forceinline__ float bf16_rne(float x) {
+  uint32_t u = __float_as_uint(x);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (x + k1 * x * x * x);
+  // tanh(u) = 1 - 2 / (1 + exp(2u))
+  const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
+  return 0.5f * x * (1.0f + t);
+}
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float u = k0 * (x + k1 * x * x * x);

@@ -32,7 +32,8 @@ SIGNATURES = {
     "svr2_txt_window_mean_bf16": [_P, _P, c_int, c_int, c_int, _P],
     "svr2_patchify_bf16": [_P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "svr2_unpatchify_bf16": [_P, c_int, _P, c_int, c_int, c_int, c_int, _P],
-    "svr2_groupnorm_bf16": [_P, _P, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, c_int, _P, _P],
+    "svr2_groupnorm_bf16": [_P, _P, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, c_int, _P, c_int64, _P],
+    "svr2_groupnorm_scratch_bytes": [c_int, c_int, c_int],
     "svr2_softmax_rows_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, _P],
     "svr2_transpose_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, _P],
     "svr2_ncdhw_to_ndhwc_bf16": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_float, _P],
@@ -58,7 +59,7 @@ def load() -> ctypes.CDLL:
         lib.svr2_last_error.argtypes = []
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
-            fn.restype = c_int
+            fn.restype = c_int64 if name.endswith("_bytes") else c_int
             fn.argtypes = args
         _lib = lib
     return _lib
@@ -78,7 +79,7 @@ def stream():
 
 
 # kernels launched per C-ABI call (for the bench's gpu_launches count)
-KERNELS_PER_CALL = {"svr2_groupnorm_bf16": 2}
+KERNELS_PER_CALL = {"svr2_groupnorm_bf16": 3}
 
 
 class Profiler:

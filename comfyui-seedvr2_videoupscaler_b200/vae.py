@@ -121,11 +121,13 @@ class B200VideoVAE:
     # ---- primitive wrappers ----------------------------------------------
     def _gn(self, x: Act, prefix: str, silu: bool, pad: int) -> Act:
         y = Act(x.T, x.H, x.W, x.C, pad, self.device)
-        if self._stats is None or self._stats.numel() < x.T * 64:
-            self._stats = torch.empty(max(x.T, 64) * 64, device=self.device, dtype=torch.float64)
+        need = lib.load().svr2_groupnorm_scratch_bytes(x.T, x.H * x.W, x.C)
+        if self._stats is None or self._stats.numel() * 8 < need:
+            self._stats = torch.empty((need + 7) // 8 + 1024, device=self.device, dtype=torch.float64)
         lib.call("svr2_groupnorm_bf16", c_void_p(x.body_ptr()), lib.ptr(y.buf), x.T, x.H * x.W, x.C,
                  lib.ptr(self.W[prefix + ".weight"]), lib.ptr(self.W[prefix + ".bias"]), 1e-6, int(silu), pad,
-                 int(pad > 0), lib.ptr(self._stats), lib.stream(), nbytes=6.0 * x.T * x.H * x.W * x.C)
+                 int(pad > 0), lib.ptr(self._stats), self._stats.numel() * 8, lib.stream(),
+                 nbytes=6.0 * x.T * x.H * x.W * x.C)
         return y
 
     def _conv(self, x: Act, prefix: str, *, out_pad=0, residual: Optional[Act] = None, stride_t=1, stride_hw=1,

@@ -97,9 +97,12 @@ int svr2_patchify_bf16(const void* vid, void* out, int T, int H, int W, int C, i
 int svr2_unpatchify_bf16(const void* in, int ld_in, void* out, int T, int H, int W, int C, void* stream);
 
 /* ---- K7: per-frame GroupNorm(32) (+SiLU).  causal_norm_wrapper
- * (causal_inflation_lib.py:354-409) + nn.SiLU.  x,y: [F,HW,C] NDHWC; stats: double [F,32,2] scratch. */
+ * (causal_inflation_lib.py:354-409) + nn.SiLU.  x,y: [F,HW,C] NDHWC.  Deterministic (no float atomics):
+ * block partials -> fixed-order finalize -> apply.  scratch: svr2_groupnorm_scratch_bytes() bytes, 8-aligned. */
 int svr2_groupnorm_bf16(const void* x, void* y, int frames, int hw, int C, const void* gamma, const void* beta,
-                        float eps, int silu, int out_t_pad, int out_dup_head, double* stats, void* stream);
+                        float eps, int silu, int out_t_pad, int out_dup_head, double* scratch,
+                        int64_t scratch_bytes, void* stream);
+int64_t svr2_groupnorm_scratch_bytes(int frames, int hw, int C);
 
 /* row softmax fp32 -> bf16 (VAE mid-block attention, attn_video_vae.py:656-668) */
 int svr2_softmax_rows_bf16(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, void* stream);

@@ -219,14 +219,20 @@ def test_qk_norm_rope_window(svr2lib):
     assert torch.equal(v.float(), rows[:, 2])
 
 
-@pytest.mark.parametrize("C,hw,frames,silu", [(128, 24 * 36, 3, 1), (256, 1000, 2, 1), (512, 77, 2, 0)])
+@pytest.mark.parametrize("C,hw,frames,silu", [(128, 24 * 36, 3, 1), (256, 1000, 2, 1), (512, 77, 2, 0),
+                                              (128, 300 * 200, 2, 1), (512, 20000, 1, 1)])
 def test_groupnorm(svr2lib, C, hw, frames, silu):
     x = bf(rnd(frames, hw, C, seed=1) * 2 + 0.5)
     gamma, beta = bf(rnd(C, seed=2) * 0.1 + 1), bf(rnd(C, seed=3) * 0.1)
     y = torch.zeros(2 + frames, hw, C, device=DEV, dtype=torch.bfloat16)
-    stats = torch.zeros(frames * 64, device=DEV, dtype=torch.float64)
-    svr2lib.call("svr2_groupnorm_bf16", svr2lib.ptr(x), svr2lib.ptr(y), frames, hw, C, svr2lib.ptr(gamma),
-                 svr2lib.ptr(beta), 1e-6, silu, 2, 1, svr2lib.ptr(stats), svr2lib.stream())
+    need = svr2lib.load().svr2_groupnorm_scratch_bytes(frames, hw, C)
+    stats = torch.zeros(need // 8 + 1, device=DEV, dtype=torch.float64)
+    args = (svr2lib.ptr(x), svr2lib.ptr(y), frames, hw, C, svr2lib.ptr(gamma), svr2lib.ptr(beta), 1e-6, silu, 2, 1,
+            svr2lib.ptr(stats), stats.numel() * 8, svr2lib.stream())
+    svr2lib.call("svr2_groupnorm_bf16", *args)
+    y_first = y.clone()
+    svr2lib.call("svr2_groupnorm_bf16", *args)
+    assert torch.equal(y, y_first), "groupnorm must be bit-reproducible"
     ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma.float(), beta.float(), 1e-6)
     ref = bf(ref).float()
     if silu:
