@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phases", action="store_true", help="print a per-kernel breakdown to stderr")
+    ap.add_argument("--detail", action="store_true", help="with --phases: break GEMM/conv launches down by shape")
     args = ap.parse_args()
     frames_real, H, W, desc = WORKLOADS[args.workload]
     from svr2_import import load_package
@@ -210,6 +211,7 @@ def main():
         sampler.start()
     # ---- timed region A: inputs resident in HBM, per-kernel events on the launching stream
     lib.PROFILER = lib.Profiler()
+    lib.PROFILER.detail = args.detail
     lib.LAUNCHES = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -255,9 +257,10 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     gemm_names = ("svr2_linear_bf16", "svr2_conv3d_bf16", "svr2_upsample_shuffle_bf16")
-    g_flops = sum(prof[n]["flops"] for n in gemm_names if n in prof)
-    g_ms = sum(prof[n]["ms"] for n in gemm_names if n in prof)
-    g_calls = sum(prof[n]["calls"] for n in gemm_names if n in prof)
+    is_gemm = lambda n: n.split("|")[0] in gemm_names
+    g_flops = sum(d["flops"] for n, d in prof.items() if is_gemm(n))
+    g_ms = sum(d["ms"] for n, d in prof.items() if is_gemm(n))
+    g_calls = sum(d["calls"] for n, d in prof.items() if is_gemm(n))
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
     fm = flop_model(frames_pad, H, W)
     if args.phases:
@@ -265,7 +268,7 @@ def main():
         for n, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
             extra = f"{d['flops'] / d['ms'] / 1e9:8.1f} TFLOP/s" if d["flops"] else (
                 f"{d['bytes'] / d['ms'] / 1e6:8.1f} GB/s" if d["bytes"] else "")
-            print(f"  {n:34s} calls {d['calls']:6d}  {d['ms'] / args.steps:9.2f} ms/step  {100 * d['ms'] / tot:5.1f}%  {extra}",
+            print(f"  {n:56s} calls {d['calls']:6d}  {d['ms'] / args.steps:9.2f} ms/step  {100 * d['ms'] / tot:5.1f}%  {extra}",
                   file=sys.stderr)
         print(f"  peak device memory {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", file=sys.stderr)
         print(f"  sum of kernel time {tot / args.steps:.1f} ms/step vs step {ms / args.steps:.1f} ms; model FLOPs/clip "

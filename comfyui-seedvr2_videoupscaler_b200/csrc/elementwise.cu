@@ -46,12 +46,11 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
@@ -60,48 +59,56 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------ RMSNorm + AdaSingle "in"
-// one block (256 threads) per row; dim % 8 == 0, dim <= 256*8*kVec
+// one warp per row (8 rows per block): all of a row's 16-byte vectors are loaded up front (kVec per lane
+// in flight), fp32 statistics by warp shuffle, one write.  dim % 8 == 0, dim <= 32*8*kVec.
 template <int kVec>
 __global__ void __launch_bounds__(256) rmsnorm_ada_kernel(const __nv_bfloat16* __restrict__ x,
-                                                          __nv_bfloat16* __restrict__ y, int dim, float eps,
+                                                          __nv_bfloat16* __restrict__ y, int rows, int dim, float eps,
                                                           const float* __restrict__ weight,
                                                           const float* __restrict__ scale,
                                                           const float* __restrict__ shift, int mode) {
-  __shared__ float red[8];
-  const long long row = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * dim);
   uint4* yr = reinterpret_cast<uint4*>(y + row * dim);
   const int nvec = dim / 8;
-  float v[kVec][8];
+  uint4 raw[kVec];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const int c = lane + i * 32;
+    raw[i] = c < nvec ? xr[c] : make_uint4(0, 0, 0, 0);
+  }
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
-    const int c = threadIdx.x + i * 256;
-    if (c < nvec) {
-      unpack8(xr[c], v[i]);
+    float v[8];
+    unpack8(raw[i], v);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) ss += v[i][e] * v[i][e];
-    }
+    for (int e = 0; e < 8; ++e) ss += v[e] * v[e];
   }
-  ss = block_sum<8>(ss, red);
+  ss = warp_sum(ss);
   const float rrms = 1.0f / sqrtf(ss / (float)dim + eps);
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
-    const int c = threadIdx.x + i * 256;
+    const int c = lane + i * 32;
     if (c < nvec) {
-      float o[8];
+      float v[8], o[8];
+      unpack8(raw[i], v);
+      const float4 s0 = *reinterpret_cast<const float4*>(scale + c * 8), s1 = *reinterpret_cast<const float4*>(scale + c * 8 + 4);
+      const float4 h0 = *reinterpret_cast<const float4*>(shift + c * 8), h1 = *reinterpret_cast<const float4*>(shift + c * 8 + 4);
+      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int ch = c * 8 + e;
-        // reference divides: x / sqrt(mean + eps)
-        float r = v[i][e] * rrms;
-        if (weight) r *= weight[ch];
+        float r = v[e] * rrms;
+        if (weight) r *= weight[c * 8 + e];
         if (mode == 0) {
-          o[e] = r * scale[ch] + shift[ch];
+          o[e] = r * sc[e] + sh[e];
         } else {
           r = bf16_round(r);
-          r = bf16_round(r * scale[ch]);
-          o[e] = r + shift[ch];
+          r = bf16_round(r * sc[e]);
+          o[e] = r + sh[e];
         }
       }
       yr[c] = pack8(o);
@@ -339,8 +346,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
       unpack8(r[u], v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float t = bf16_round(v[e] * ca[e] + cb[e]);   // F.group_norm output is bf16
-        o[e] = silu ? silu_f(t) : t;
+        const float t = bf16_rne(v[e] * ca[e] + cb[e]);   // F.group_norm output is bf16
+        o[e] = silu ? silu_fast(t) : t;
       }
       const uint4 pk = pack8(o);
       reinterpret_cast<uint4*>(yf)[i + u * stride] = pk;
@@ -355,8 +362,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
     unpack8(reinterpret_cast<const uint4*>(xf)[i], v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float t = bf16_round(v[e] * ca[e] + cb[e]);
-      o[e] = silu ? silu_f(t) : t;
+      const float t = bf16_rne(v[e] * ca[e] + cb[e]);
+      o[e] = silu ? silu_fast(t) : t;
     }
     const uint4 pk = pack8(o);
     reinterpret_cast<uint4*>(yf)[i] = pk;
@@ -392,6 +399,26 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
                          pack_bf16x2(__expf(v.z - m) * inv, __expf(v.w - m) * inv));
     *reinterpret_cast<uint2*>(pr + c) = o;
   }
+}
+
+// ------------------------------------------------------------------ attention pass-1 combine
+// partial [rows][slots] (max, sum exp2) -> lse2[row] = M + log2(sum_i l_i 2^(m_i - M))
+__global__ void rowstat_combine_kernel(const float2* __restrict__ part, int slots, long long ld, float* __restrict__ lse,
+                                       int rows) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float2* pr = part + row * ld;
+  float mx = -INFINITY;
+  for (int i = lane; i < slots; i += 32) mx = fmaxf(mx, pr[i].x);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int i = lane; i < slots; i += 32) {
+    const float2 v = pr[i];
+    if (v.x > -INFINITY) s += v.y * exp2f(v.x - mx);
+  }
+  s = warp_sum(s);
+  if (lane == 0) lse[row] = mx + log2f(s);
 }
 
 // ------------------------------------------------------------------ transpose bf16 [rows, cols] -> [cols, rows]
@@ -452,21 +479,32 @@ __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ in, int 
 }
 
 // 3x3x3 im2col, zero spatial padding, causal halo = 2 real frames in front of x.
-// x [2+T, H, W, ld_in] (C real channels) -> out [T*H*W, ld_out], column ((kt*3+kh)*3+kw)*C + c
-__global__ void im2col3_kernel(const __nv_bfloat16* __restrict__ x, int T, int H, int W, int C, int ld_in,
-                               __nv_bfloat16* __restrict__ out, int ld_out) {
-  const long long total = (long long)T * H * W;
-  const long long row = blockIdx.x;
-  if (row >= total) return;
-  const int w = row % W, h = (row / W) % H, t = row / ((long long)W * H);
-  for (int i = threadIdx.x; i < ld_out; i += blockDim.x) {
-    __nv_bfloat16 val = __float2bfloat16(0.f);
-    if (i < 27 * C) {
-      const int c = i % C, tap = i / C, kw = tap % 3, kh = (tap / 3) % 3, kt = tap / 9;
-      const int hh = h + kh - 1, ww = w + kw - 1, tt = t + kt;  // halo offset already included
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = x[(((long long)tt * H + hh) * W + ww) * ld_in + c];
+// x [2+T, H, W, ld_in] (C real channels) -> out [T*H*W, ld_out], column ((kt*3+kh)*3+kw)*C + c.
+// One thread produces one 16-byte chunk (8 consecutive columns) of an output row.
+__global__ void __launch_bounds__(256) im2col3_kernel(const __nv_bfloat16* __restrict__ x, int T, int H, int W, int C,
+                                                      int ld_in, __nv_bfloat16* __restrict__ out, int ld_out) {
+  const int cpr = ld_out / 8;
+  const long long total = (long long)T * H * W * cpr;
+  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / cpr;
+    const int c8 = (int)(idx - row * cpr) * 8;
+    const int w = row % W, h = (row / W) % H, t = row / ((long long)W * H);
+    unsigned short v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = c8 + e;
+      v[e] = 0;
+      if (i < 27 * C) {
+        const int tap = i / C, c = i - tap * C, kw = tap % 3, kh = (tap / 3) % 3, kt = tap / 9;
+        const int hh = h + kh - 1, ww = w + kw - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v[e] = xs[(((long long)(t + kt) * H + hh) * W + ww) * ld_in + c];
+      }
     }
-    out[row * ld_out + i] = val;
+    uint4 pk = make_uint4(v[0] | (uint32_t(v[1]) << 16), v[2] | (uint32_t(v[3]) << 16), v[4] | (uint32_t(v[5]) << 16),
+                          v[6] | (uint32_t(v[7]) << 16));
+    reinterpret_cast<uint4*>(out + row * ld_out)[c8 / 8] = pk;
   }
 }
 
@@ -476,13 +514,16 @@ using namespace svr2;
 
 extern "C" int svr2_rmsnorm_ada_bf16(const void* x, void* y, int rows, int dim, float eps, const float* weight,
                                      const float* scale, const float* shift, int mode, void* stream) {
-  if (dim % 8 || dim > 256 * 8 * 2) return set_error(SVR2_ERR_ARG, "svr2_rmsnorm_ada_bf16: dim % 8 != 0 or dim > 4096");
+  if (dim % 8 || dim > 32 * 8 * 16) return set_error(SVR2_ERR_ARG, "svr2_rmsnorm_ada_bf16: dim % 8 != 0 or dim > 4096");
   if (rows <= 0) return SVR2_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (dim <= 2048)
-    rmsnorm_ada_kernel<1><<<rows, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, dim, eps, weight, scale, shift, mode);
-  else
-    rmsnorm_ada_kernel<2><<<rows, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, dim, eps, weight, scale, shift, mode);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
+  __nv_bfloat16* yo = (__nv_bfloat16*)y;
+  if (dim <= 1024) rmsnorm_ada_kernel<4><<<grid, 256, 0, s>>>(xi, yo, rows, dim, eps, weight, scale, shift, mode);
+  else if (dim <= 2560) rmsnorm_ada_kernel<10><<<grid, 256, 0, s>>>(xi, yo, rows, dim, eps, weight, scale, shift, mode);
+  else if (dim <= 3072) rmsnorm_ada_kernel<12><<<grid, 256, 0, s>>>(xi, yo, rows, dim, eps, weight, scale, shift, mode);
+  else rmsnorm_ada_kernel<16><<<grid, 256, 0, s>>>(xi, yo, rows, dim, eps, weight, scale, shift, mode);
   return check_launch("rmsnorm_ada");
 }
 
@@ -568,6 +609,12 @@ extern "C" int svr2_softmax_rows_bf16(const float* s, int64_t lds, void* p, int6
   return check_launch("softmax_rows");
 }
 
+extern "C" int svr2_rowstat_combine(const void* partial, int slots, int64_t ld, float* lse, int rows, void* stream) {
+  if (rows <= 0) return SVR2_OK;
+  rowstat_combine_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const float2*)partial, slots, ld, lse, rows);
+  return check_launch("rowstat_combine");
+}
+
 extern "C" int svr2_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols,
                                    void* stream) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
@@ -600,7 +647,10 @@ extern "C" int svr2_ndhwc_to_ncdhw(const void* in, int ld_in, int C, int T, int 
 }
 extern "C" int svr2_im2col3_bf16(const void* x, int T, int H, int W, int C, int ld_in, void* out, int ld_out,
                                  void* stream) {
-  const long long total = (long long)T * H * W;
-  im2col3_kernel<<<(unsigned)total, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, T, H, W, C, ld_in, (__nv_bfloat16*)out, ld_out);
+  if (ld_out % 8) return set_error(SVR2_ERR_ARG, "im2col3: ld_out % 8");
+  const long long total = (long long)T * H * W * (ld_out / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  im2col3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, T, H, W, C, ld_in, (__nv_bfloat16*)out, ld_out);
   return check_launch("im2col3");
 }

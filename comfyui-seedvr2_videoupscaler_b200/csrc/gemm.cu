@@ -73,6 +73,8 @@ enum : int {
   EPI_F32 = 32,       // fp32 output = acc * out_scale (no rounding)
   EPI_SHUFFLE = 64,   // Upsample3D pixel shuffle store
   EPI_SILU = 128,     // t = bf16(silu(t))
+  EPI_ROWSTAT = 256,  // out: per (row, n-tile half) partial (max, sum exp2) of acc*out_scale  (attention pass 1)
+  EPI_PEXP = 512,     // out: bf16(exp2(acc*out_scale - rowvec[m]))                         (attention pass 2)
 };
 
 template <int BLOCK_N>
@@ -88,7 +90,7 @@ struct SmemLayout {
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
-enum : int { KIND_BF16 = 0, KIND_SWIGLU = 1, KIND_F32 = 2 };
+enum : int { KIND_BF16 = 0, KIND_SWIGLU = 1, KIND_F32 = 2, KIND_ROWSTAT = 3, KIND_PEXP = 4 };
 
 // One tile's output row of a thread: destination offset (elements), validity, halo duplication.
 struct RowDest {
@@ -138,7 +140,10 @@ __device__ __forceinline__ RowDest row_dest(const GemmParams& p, int m_blk, int 
   return d;
 }
 
-template <int BLOCK_N, int KIND>
+// SWAP (conv only, BLOCK_N = 256): operands exchanged so that M = 128 output channels (weights as A)
+// and N = 256 output pixels (activation box as B).  Cout = 128 layers then run 128x256 tiles instead of
+// 128x128 ones, whose SS-MMA shared-memory read rate (128 B/clk) caps them near 1 PFLOP/s.
+template <int BLOCK_N, int KIND, bool SWAP = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
@@ -221,7 +226,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int t_o = m_blk / per_frame, r = m_blk - t_o * per_frame;
           const int th = r / tiles_w;
           const int h0 = th * bh, w0 = (r - th * tiles_w) * bw;
-          const int n0 = n_blk * BLOCK_N;
+          const int n0 = n_blk * (SWAP ? BLOCK_M : BLOCK_N);
           int kcol = 0;
           for (int kt_ = 0; kt_ < taps_t; ++kt_) {
             const int t_in = t_o * stride_t + kt_;
@@ -230,14 +235,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int cb = 0; cb < cin_blocks; ++cb) {
                   uint8_t* sa; uint64_t* fb;
                   acquire(sa, fb);
+                  uint8_t* s_act = SWAP ? sa + L::kABytes : sa;      // activation box
+                  uint8_t* s_wgt = SWAP ? sa : sa + L::kABytes;      // weight rows
                   if (a_mode == 1) {
-                    tma_load_4d(sa, &tmap_a, fb, cb * BLOCK_K, w0 + kw_ - pad_w, h0 + kh_ - pad_h, t_in);
+                    tma_load_4d(s_act, &tmap_a, fb, cb * BLOCK_K, w0 + kw_ - pad_w, h0 + kh_ - pad_h, t_in);
                   } else {
                     // pair view (2C, W/2, 2, H/2, T): input pixel 2*o + k -> pair o + k/2, phase k%2
-                    tma_load_5d(sa, &tmap_a, fb, (kw_ & 1) * cin + cb * BLOCK_K, w0 + (kw_ >> 1), kh_ & 1,
+                    tma_load_5d(s_act, &tmap_a, fb, (kw_ & 1) * cin + cb * BLOCK_K, w0 + (kw_ >> 1), kh_ & 1,
                                 h0 + (kh_ >> 1), t_in);
                   }
-                  tma_load_2d(sa + L::kABytes, &tmap_b, fb, kcol, n0);
+                  tma_load_2d(s_wgt, &tmap_b, fb, kcol, n0);
                   kcol += BLOCK_K;
                   advance();
                 }
@@ -309,6 +316,73 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n_tiles, n_blk = tile - m_blk * num_n_tiles;
+      if constexpr (SWAP) {
+        // accumulator lanes = output channels (this thread: co), columns = the tile's 256 pixels.
+        const int per_frame = p.tiles_w * p.tiles_h;
+        const int t_o = m_blk / per_frame, r = m_blk - t_o * per_frame;
+        const int th = r / p.tiles_w;
+        const int h0 = th * p.bh, w0 = (r - th * p.tiles_w) * p.bw;
+        const int co = n_blk * BLOCK_M + row;
+        const float bsc = ((epi & EPI_BIAS) && co < p.N) ? __bfloat162float(bias[co]) : 0.f;
+        const long long fbase = (long long)(t_o + p.out_t_pad) * p.out_frame_stride + n_blk * BLOCK_M + q * 32;
+        const bool dup_t = p.out_dup_head && t_o == 0;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_STRIDE;
+        unsigned short* slab16 = reinterpret_cast<unsigned short*>(slab);
+#pragma unroll 1
+        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          if (c0 + 32 >= half * 128 + 128) {
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+          // transpose through the slab: row = pixel (128 B stride), 32 channels (64 B) per row
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            slab16[j * 64 + lane] = (unsigned short)(__float_as_uint(bf16_rne(__uint_as_float(v[j]) + bsc)) >> 16);
+          __syncwarp();
+          const int chn = lane & 3, psub = lane >> 2;          // 4 lanes x 16 B per pixel, 8 pixels per access
+          long long off[4];
+          int flags[4];
+          uint4 rv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int pj = c0 + i * 8 + psub;                  // pixel index within the tile
+            const int ph = pj / p.bw, pw = pj - ph * p.bw;
+            const int h = h0 + ph, w = w0 + pw;
+            const bool ok = (h < p.H_out) && (w < p.W_out) && (n_blk * BLOCK_M + q * 32 + chn * 8 < p.N);
+            off[i] = fbase + ((long long)h * p.W_out + w) * p.ldc + chn * 8;
+            flags[i] = ok ? (dup_t ? 3 : 1) : 0;
+            if ((epi & EPI_RESIDUAL) && ok) rv[i] = *reinterpret_cast<const uint4*>(resid + off[i]);
+          }
+          __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (!(flags[i] & 1)) continue;
+            uint4 d = *reinterpret_cast<const uint4*>(slab + (i * 8 + psub) * 128 + chn * 16);
+            if (epi & EPI_RESIDUAL) {
+              const uint32_t dw[4] = {d.x, d.y, d.z, d.w}, rw[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o[e] = pack_bf16x2(__uint_as_float(dw[e] << 16) + __uint_as_float(rw[e] << 16),
+                                   __uint_as_float(dw[e] & 0xffff0000u) + __uint_as_float(rw[e] & 0xffff0000u));
+              d = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            *reinterpret_cast<uint4*>(ob + off[i]) = d;
+            if (flags[i] & 2) {
+              *reinterpret_cast<uint4*>(ob + off[i] - p.out_frame_stride) = d;
+              *reinterpret_cast<uint4*>(ob + off[i] - 2 * p.out_frame_stride) = d;
+            }
+          }
+          __syncwarp();
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       const RowDest dst = row_dest<BLOCK_N>(p, m_blk, n_blk, row, N_COLS);
       const int n_base = n_blk * (KIND == KIND_SWIGLU ? BLOCK_N / 2 : BLOCK_N);   // first output column
 
@@ -316,7 +390,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_STRIDE;
 
-      if (!active) {
+      float row_lse = 0.f;
+      if constexpr (KIND == KIND_PEXP) {
+        const int m = m_blk * BLOCK_M + row;
+        row_lse = (m < p.M) ? gate[m] : 0.f;
+      }
+      if constexpr (KIND == KIND_ROWSTAT) {
+        // attention pass 1: thread-local online (max, sum exp2) over this warp's columns; no staging
+        float mx = -INFINITY, sum = 0.f;
+        if (active) {
+          const float sc = p.out_scale;
+#pragma unroll 1
+          for (int c0 = col_lo; c0 < col_lo + COLS_W; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(t_addr + c0, v);
+            tmem_ld_wait();
+            const int n0 = n_base + c0;
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float t = (n0 + j < p.N) ? __uint_as_float(v[j]) * sc : -INFINITY;
+              v[j] = __float_as_uint(t);
+              cm = fmaxf(cm, t);
+            }
+            const float m_new = fmaxf(mx, cm);
+            if (m_new > -INFINITY) {
+              float cs = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) cs += exp2_approx(__uint_as_float(v[j]) - m_new);
+              sum = sum * exp2_approx(mx - m_new) + cs;
+              mx = m_new;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+        const int m = m_blk * BLOCK_M + row;
+        if (active && m < p.M) {
+          const int slot = (N_COLS >= 64) ? n_blk * 2 + half : n_blk;
+          reinterpret_cast<float2*>(p.out)[(long long)m * p.ldc + slot] = make_float2(mx, sum);
+        }
+      } else if (!active) {
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
       } else {
@@ -342,6 +456,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               const float sc = p.out_scale;
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * sc);
+            } else if constexpr (KIND == KIND_PEXP) {
+              tmem_ld_wait();
+              const float sc = p.out_scale;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                v[j] = __float_as_uint(bf16_rne(exp2_approx(__uint_as_float(v[j]) * sc - row_lse)));
             } else {
               tmem_ld_wait();
               // per-column operands, 8 columns at a time (N % 8 == 0: a group is all-valid or all-OOB)
@@ -523,12 +643,12 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BLOCK_N, int KIND>
+template <int BLOCK_N, int KIND, bool SWAP = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, KIND>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, KIND, SWAP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
     configured = true;
@@ -536,7 +656,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid <= 0) return SVR2_OK;
-  gemm_tcgen05_kernel<BLOCK_N, KIND><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
+  gemm_tcgen05_kernel<BLOCK_N, KIND, SWAP><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
   return SVR2_OK;
@@ -547,6 +667,18 @@ static int dispatch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& 
   if (p.epi & EPI_SWIGLU) {
     if (block_n == 256) return launch_gemm<256, KIND_SWIGLU>(ta, tb, p, s);
     return set_error(SVR2_ERR_ARG, "SwiGLU epilogue needs BLOCK_N = 256");
+  }
+  if (p.epi & EPI_ROWSTAT) {
+    if (block_n == 256) return launch_gemm<256, KIND_ROWSTAT>(ta, tb, p, s);
+    if (block_n == 128) return launch_gemm<128, KIND_ROWSTAT>(ta, tb, p, s);
+    if (block_n == 64) return launch_gemm<64, KIND_ROWSTAT>(ta, tb, p, s);
+    return launch_gemm<32, KIND_ROWSTAT>(ta, tb, p, s);
+  }
+  if (p.epi & EPI_PEXP) {
+    if (block_n == 256) return launch_gemm<256, KIND_PEXP>(ta, tb, p, s);
+    if (block_n == 128) return launch_gemm<128, KIND_PEXP>(ta, tb, p, s);
+    if (block_n == 64) return launch_gemm<64, KIND_PEXP>(ta, tb, p, s);
+    return launch_gemm<32, KIND_PEXP>(ta, tb, p, s);
   }
   if (p.epi & EPI_F32) {
     switch (block_n) {
@@ -569,6 +701,7 @@ static int dispatch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& 
 
 static int pick_block_n(int N, int epi) {
   if (epi & EPI_SWIGLU) return 256;
+  if ((epi & (EPI_ROWSTAT | EPI_PEXP)) && N <= 32) return 32;
   if (N >= 256) return 256;
   if (N > 64) return 128;
   if (N > 32) return 64;
@@ -587,9 +720,10 @@ extern "C" int svr2_linear_bf16(const void* a, int64_t lda, const void* w, int64
                                 int epi_flags, const void* bias, const float* gate, const void* residual, void* out,
                                 int64_t ldc, float out_scale, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(SVR2_ERR_ARG, "svr2_linear_bf16: empty problem");
-  const bool f32 = (epi_flags & EPI_F32) != 0;
-  if ((lda % 8) || (ldw % 8) || (ldc % (f32 ? 4 : 8)) || (N % (f32 ? 4 : 8)))
+  const bool f32 = (epi_flags & EPI_F32) != 0, rowstat = (epi_flags & EPI_ROWSTAT) != 0;
+  if ((lda % 8) || (ldw % 8) || (!rowstat && ((ldc % (f32 ? 4 : 8)) || (N % (f32 ? 4 : 8)))))
     return set_error(SVR2_ERR_ARG, "svr2_linear_bf16: lda/ldw must be multiples of 8, ldc/N of 8 (4 for fp32 out)");
+  if ((epi_flags & EPI_PEXP) && !gate) return set_error(SVR2_ERR_ARG, "EPI_PEXP needs the row log-sum-exp vector (gate)");
   if ((epi_flags & EPI_SWIGLU) && (N % 256)) return set_error(SVR2_ERR_ARG, "SwiGLU needs N % 256 == 0");
   const int bn = pick_block_n(N, epi_flags);
   CUtensorMap ta, tb;
@@ -616,8 +750,16 @@ extern "C" int svr2_linear_bf16(const void* a, int64_t lda, const void* w, int64
   p.out = out;
   if ((p.epi & EPI_BIAS) && !bias) return set_error(SVR2_ERR_ARG, "EPI_BIAS without bias");
   if ((p.epi & EPI_GATE) && !gate) return set_error(SVR2_ERR_ARG, "EPI_GATE without gate");
+  if (rowstat && ldc < (int64_t)p.num_n_tiles * (bn >= 64 ? 2 : 1))
+    return set_error(SVR2_ERR_ARG, "EPI_ROWSTAT: ldc (float2 slots per row) must be >= svr2_rowstat_slots(N)");
   if ((p.epi & EPI_RESIDUAL) && !residual) return set_error(SVR2_ERR_ARG, "EPI_RESIDUAL without residual");
   return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream);
+}
+
+// number of (max, sum) float2 partial slots per row that EPI_ROWSTAT writes for a given N
+extern "C" int svr2_rowstat_slots(int N) {
+  const int bn = pick_block_n(N, EPI_ROWSTAT);
+  return ((N + bn - 1) / bn) * (bn >= 64 ? 2 : 1);
 }
 
 // Causal Conv3d as implicit GEMM.  x: NDHWC bf16 with `in_t_pad` halo frames in front
@@ -632,12 +774,19 @@ extern "C" int svr2_conv3d_bf16(const void* x, int T_in_total, int H, int W, int
   if (stride_hw != 1 && stride_hw != 2) return set_error(SVR2_ERR_ARG, "stride_hw must be 1 or 2");
   const int H_out = stride_hw == 1 ? H : H / 2, W_out = stride_hw == 1 ? W : W / 2;
   if (stride_hw == 2 && ((H | W) & 1)) return set_error(SVR2_ERR_ARG, "stride-2 conv needs even H, W");
-  // tile shape: bw x bh = 128 output pixels
+  // Cout <= 128: swap operands (128 channels x 256 pixels per tile); else 128 pixels x up to 256 channels
+  const bool swap = (Cout > 64 && Cout <= 128) && (long long)H_out * W_out >= 256;
+  // tile shape: bw x bh output pixels (128, or 256 when swapped)
   int bw = 16, bh = 8;
-  if (W_out >= 128 && H_out < 8) { bw = 128; bh = 1; }
-  else if (W_out <= 8) { bw = 8; bh = 16; }
-  else if (W_out <= 4) { bw = 4; bh = 32; }
-  const int bn = pick_block_n(Cout, 0);
+  if (swap) {
+    bw = 32; bh = 8;
+    if (W_out <= 16) { bw = 16; bh = 16; }
+    if (W_out <= 8) { bw = 8; bh = 32; }
+  } else {
+    if (W_out >= 128 && H_out < 8) { bw = 128; bh = 1; }
+    else if (W_out <= 8) { bw = 8; bh = 16; }
+  }
+  const int bn = swap ? 128 : pick_block_n(Cout, 0);
   CUtensorMap ta, tb;
   int rc;
   if (stride_hw == 1) {
@@ -680,6 +829,7 @@ extern "C" int svr2_conv3d_bf16(const void* x, int T_in_total, int H, int W, int
   p.bias = (const __nv_bfloat16*)bias;
   p.residual = (const __nv_bfloat16*)residual;
   p.out = y;
+  if (swap) return launch_gemm<256, KIND_BF16, true>(ta, tb, p, (cudaStream_t)stream);
   return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream);
 }
 

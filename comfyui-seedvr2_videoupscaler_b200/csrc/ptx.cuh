@@ -201,6 +201,11 @@ __device__ __forceinline__ float bf16_rne(float x) {
   u += 0x7fffu + ((u >> 16) & 1u);
   return __uint_as_float(u & 0xffff0000u);
 }
+__device__ __forceinline__ float exp2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;

@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libsvr2.so")
 
 EPI_BIAS, EPI_GATE, EPI_RESIDUAL, EPI_SWIGLU, EPI_GELU, EPI_F32, EPI_SILU = 1, 2, 4, 8, 16, 32, 128
+EPI_ROWSTAT, EPI_PEXP = 256, 512
 
 # name -> argtypes; every function returns int (svr2_status) except svr2_last_error
 _P = c_void_p
@@ -35,6 +36,8 @@ SIGNATURES = {
     "svr2_groupnorm_bf16": [_P, _P, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, c_int, _P, c_int64, _P],
     "svr2_groupnorm_scratch_bytes": [c_int, c_int, c_int],
     "svr2_softmax_rows_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, _P],
+    "svr2_rowstat_slots": [c_int],
+    "svr2_rowstat_combine": [_P, c_int, c_int64, _P, c_int, _P],
     "svr2_transpose_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, _P],
     "svr2_ncdhw_to_ndhwc_bf16": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_float, _P],
     "svr2_ndhwc_to_ncdhw": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
@@ -89,6 +92,7 @@ class Profiler:
     def __init__(self):
         self.records = []      # (name, flops, bytes, start_event, end_event)
         self.launches = 0
+        self.detail = False    # tag GEMM/conv records with their shapes
 
     def summary(self):
         torch.cuda.synchronize()
@@ -110,7 +114,7 @@ PROFILER = None
 LAUNCHES = 0
 
 
-def call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0):
+def call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0, tag: str = ""):
     global LAUNCHES
     LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     prof = PROFILER
@@ -119,7 +123,7 @@ def call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0):
         e0.record()
         _check(getattr(load(), name)(*args), name)
         e1.record()
-        prof.records.append((name, flops, nbytes, e0, e1))
+        prof.records.append((name + tag, flops, nbytes, e0, e1))
     else:
         _check(getattr(load(), name)(*args), name)
 
@@ -147,7 +151,8 @@ def linear(a, w, *, bias=None, gate=None, residual=None, epi=0, out=None, out_sc
     if bias is not None:
         epi |= EPI_BIAS
     if gate is not None:
-        epi |= EPI_GATE
+        if not epi & EPI_PEXP:
+            epi |= EPI_GATE
         assert gate.dtype == torch.float32
     if residual is not None:
         epi |= EPI_RESIDUAL
@@ -156,9 +161,11 @@ def linear(a, w, *, bias=None, gate=None, residual=None, epi=0, out=None, out_sc
         out = torch.empty(M, n_out, device=a.device, dtype=torch.float32 if epi & EPI_F32 else torch.bfloat16)
     if residual is not None:
         assert residual.stride(0) == out.stride(0)
+    ldc = out.stride(0) // 2 if epi & EPI_ROWSTAT else out.stride(0)   # ROWSTAT: float2 slots per row
     call("svr2_linear_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epi, ptr(bias), ptr(gate),
-         ptr(residual), ptr(out), out.stride(0), float(out_scale), stream(),
-         flops=2.0 * M * (n_valid if n_valid is not None else N) * K)
+         ptr(residual), ptr(out), ldc, float(out_scale), stream(),
+         flops=2.0 * M * (n_valid if n_valid is not None else N) * K,
+         tag=f"|{M}x{N}x{K}|e{epi}" if (PROFILER is not None and PROFILER.detail) else "")
     return out
 
 

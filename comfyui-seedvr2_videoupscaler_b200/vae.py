@@ -151,7 +151,9 @@ class B200VideoVAE:
                  stride_t, stride_hw, pad_hw, T_out, epi, lib.ptr(self.W[prefix + ".bias"]), res_ptr, lib.ptr(y.buf),
                  out_pad, int(out_pad > 0), w.shape[0], lib.stream(),
                  flops=2.0 * T_out * Ho * Wo * self.W[prefix + ".weight.real"][0] * kt * kh * kw
-                 * self.W[prefix + ".weight.real"][1])
+                 * self.W[prefix + ".weight.real"][1],
+                 tag=(f"|{Cin}>{w.shape[0]}|k{kt}{kh}{kw}|s{stride_t}{stride_hw}|{T_out}x{Ho}x{Wo}"
+                      if (lib.PROFILER is not None and lib.PROFILER.detail) else ""))
         return y
 
     def _resnet(self, x: Act, p: str, out_pad=0) -> Act:
@@ -173,24 +175,38 @@ class B200VideoVAE:
         y = self._gn(x, p + "group_norm", False, 0)
         yf = y.buf.view(x.T * n, C)
         q = lib.linear(yf, self.W[p + "to_q.weight"], bias=self.W[p + "to_q.bias"])
-        k = lib.linear(yf, self.W[p + "to_k.weight"], bias=self.W[p + "to_k.bias"])
+        ldn = (n + 7) // 8 * 8
+        # K carries 8 spare rows: pass 2 runs with N rounded up to a multiple of 8 (16-byte stores);
+        # the extra score columns are never read by the P @ V GEMM (its K extent is n)
+        k_buf = torch.empty(x.T * n + 8, C, device=dev, dtype=torch.bfloat16)
+        k_buf[x.T * n:].zero_()
+        k_ = lib.linear(yf, self.W[p + "to_k.weight"], bias=self.W[p + "to_k.bias"], out=k_buf[: x.T * n])
         v = lib.linear(yf, self.W[p + "to_v.weight"], bias=self.W[p + "to_v.bias"])
         del y, yf
+        # Two GEMM passes per query chunk, never materialising the fp32 score matrix:
+        #   pass 1: per-row (max, sum exp2) partials of q k^T * scale  -> log2-sum-exp per row
+        #   pass 2: P = bf16(exp2(q k^T * scale - lse))  (normalised probabilities)
+        #   then   O = P @ V  (V consumed through its transpose, K-major)
         ldn = (n + 7) // 8 * 8
-        cq = max(128, min(n, (1 << 28) // max(n, 1)) // 128 * 128)   # S chunk <= 1 GiB fp32
-        cq = min(cq, (n + 127) // 128 * 128)
+        wave_rows = 74 * 128                       # 74 m-tiles x 2 n-tiles (d = 512) = one full wave of 148 CTAs
+        k = max(1, (1 << 32) // (wave_rows * ldn * 2))
+        cq = min(wave_rows * k, (n + 127) // 128 * 128)
+        slots = lib.load().svr2_rowstat_slots(n)
         vt = torch.empty(C, ldn, device=dev, dtype=torch.bfloat16)
-        S = torch.empty(min(cq, n), n, device=dev, dtype=torch.float32)
+        part = torch.empty(min(cq, n), 2 * slots, device=dev, dtype=torch.float32)
+        lse = torch.empty(min(cq, n), device=dev, dtype=torch.float32)
         P = torch.empty(min(cq, n), ldn, device=dev, dtype=torch.bfloat16)
         o = torch.empty(x.T * n, C, device=dev, dtype=torch.bfloat16)
-        scale = 1.0 / (C ** 0.5)
+        scale2 = (1.0 / (C ** 0.5)) * 1.4426950408889634
         for f in range(x.T):
-            qf, kf, vf = q[f * n:(f + 1) * n], k[f * n:(f + 1) * n], v[f * n:(f + 1) * n]
+            qf, kf, vf = q[f * n:(f + 1) * n], k_[f * n:(f + 1) * n], v[f * n:(f + 1) * n]
             lib.call("svr2_transpose_bf16", lib.ptr(vf), C, lib.ptr(vt), ldn, n, C, lib.stream())
             for r0 in range(0, n, cq):
                 rows = min(cq, n - r0)
-                lib.linear(qf[r0:r0 + rows], kf, epi=lib.EPI_F32, out=S[:rows], out_scale=scale)
-                lib.call("svr2_softmax_rows_bf16", lib.ptr(S), n, lib.ptr(P), ldn, rows, n, lib.stream())
+                lib.linear(qf[r0:r0 + rows], kf, epi=lib.EPI_ROWSTAT, out=part[:rows], out_scale=scale2)
+                lib.call("svr2_rowstat_combine", lib.ptr(part), slots, slots, lib.ptr(lse), rows, lib.stream())
+                lib.linear(qf[r0:r0 + rows], k_buf[f * n: f * n + ldn], epi=lib.EPI_PEXP, gate=lse, out=P[:rows],
+                           out_scale=scale2)
                 lib.linear(P[:rows, :n], vt[:, :n], out=o[f * n + r0: f * n + r0 + rows])
         out = Act(x.T, x.H, x.W, C, 0, dev)
         xb = x.body.reshape(x.T * n, C)

@@ -36,6 +36,8 @@ enum svr2_epilogue {
   SVR2_EPI_GELU = 16,     /* gelu_tanh                                   dit_7b/mlp.py:35-43                   */
   SVR2_EPI_F32 = 32,      /* fp32 output = acc * out_scale (attention scores)                                  */
   SVR2_EPI_SILU = 128,    /* silu                                        embedding.py:56-60                    */
+  SVR2_EPI_ROWSTAT = 256, /* attention pass 1: out[m][slot] = (max, sum exp2) of acc*out_scale over the slot's columns   */
+  SVR2_EPI_PEXP = 512,    /* attention pass 2: out = bf16(exp2(acc*out_scale - gate[m])), gate = per-row log2-sum-exp     */
 };
 
 const char* svr2_last_error(void);
@@ -104,7 +106,12 @@ int svr2_groupnorm_bf16(const void* x, void* y, int frames, int hw, int C, const
                         int64_t scratch_bytes, void* stream);
 int64_t svr2_groupnorm_scratch_bytes(int frames, int hw, int C);
 
-/* row softmax fp32 -> bf16 (VAE mid-block attention, attn_video_vae.py:656-668) */
+/* VAE mid-block attention (1 head, d = 512; attn_video_vae.py:656-668) as two GEMM passes that never
+ * materialise the fp32 score matrix: pass 1 = svr2_linear_bf16(..., SVR2_EPI_ROWSTAT) + svr2_rowstat_combine,
+ * pass 2 = svr2_linear_bf16(..., SVR2_EPI_PEXP) writing normalised bf16 probabilities, then P @ V. */
+int svr2_rowstat_slots(int N);
+int svr2_rowstat_combine(const void* partial, int slots, int64_t ld, float* lse, int rows, void* stream);
+/* row softmax fp32 -> bf16 (materialised-score variant, kept for small problems / tests) */
 int svr2_softmax_rows_bf16(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, void* stream);
 int svr2_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols, void* stream);
 

@@ -115,6 +115,10 @@ def _to_ndhwc(x_ncdhw, halo):
     (512, 512, (3, 3, 3), 1, 1, 2, 6, 10),
     (128, 8, (3, 3, 3), 1, 1, 2, 12, 20),
     (256, 32, (3, 3, 3), 1, 1, 1, 4, 6),
+    (128, 128, (3, 3, 3), 2, 2, 5, 48, 64),      # swap-AB + pair view
+    (128, 128, (1, 3, 3), 1, 2, 2, 40, 72),      # swap-AB, spatial-only downsample
+    (256, 128, (3, 3, 3), 1, 1, 2, 30, 44),      # swap-AB, ragged tile edges
+    (128, 128, (1, 1, 1), 1, 1, 2, 24, 40),      # swap-AB 1x1x1
 ])
 def test_conv3d(svr2lib, Cin, Cout, k, st, shw, T, H, W):
     x = rnd(1, Cin, T, H, W, seed=1)
@@ -286,3 +290,26 @@ def test_layout_and_im2col(svr2lib):
     ref = xp.unfold(2, 3, 1).unfold(3, 3, 1).unfold(4, 3, 1)  # 1,C,T,H,W,kt,kh,kw
     ref = ref[0].permute(1, 2, 3, 4, 5, 6, 0).reshape(T * H * W, 81)
     assert torch.equal(col[:, :81].float(), ref) and col[:, 81:].abs().max() == 0
+
+
+@pytest.mark.parametrize("M,n", [(300, 160), (1000, 2052), (129, 36)])
+def test_two_pass_attention_probabilities(svr2lib, M, n):
+    """EPI_ROWSTAT + rowstat_combine + EPI_PEXP == softmax(q k^T * scale) (VAE mid-block attention)."""
+    d = 512
+    q, k = bf(rnd(M, d, seed=1)), bf(rnd(n, d, seed=2))
+    scale = d ** -0.5
+    s2 = scale * 1.4426950408889634
+    slots = svr2lib.load().svr2_rowstat_slots(n)
+    part = torch.empty(M, 2 * slots, device=DEV, dtype=torch.float32)
+    svr2lib.linear(q, k, epi=svr2lib.EPI_ROWSTAT, out=part, out_scale=s2)
+    lse = torch.empty(M, device=DEV, dtype=torch.float32)
+    svr2lib.call("svr2_rowstat_combine", svr2lib.ptr(part), slots, slots, svr2lib.ptr(lse), M, svr2lib.stream())
+    ldn = (n + 7) // 8 * 8
+    P = torch.zeros(M, ldn, device=DEV, dtype=torch.bfloat16)
+    k_pad = torch.zeros(ldn, d, device=DEV, dtype=torch.bfloat16)   # bf16 output needs N % 8 == 0
+    k_pad[:n] = k
+    svr2lib.linear(q, k_pad, epi=svr2lib.EPI_PEXP, gate=lse, out=P, out_scale=s2)
+    S = (q.float() @ k.float().T) * scale
+    assert_close(lse, torch.logsumexp(S, -1) * 1.4426950408889634, 1e-4, "lse2")
+    assert_close(P[:, :n], torch.softmax(S, -1), 6e-3, "probabilities")
+    assert (P[:, :n].float().sum(-1) - 1).abs().max() < 2e-2
