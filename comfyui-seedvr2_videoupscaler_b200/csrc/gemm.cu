@@ -8,7 +8,7 @@
 // temporal halo is two real frames stored in front of every activation tensor).
 //
 // Roles (384 threads, 1 CTA / SM, grid = #SMs, static tile schedule):
-//   warp 0 : TMA producer   (kStages-deep smem ring, 128B-swizzled K-major tiles)
+//   warps 0,3 : TMA producers (even / odd k-blocks of a kStages-deep smem ring, 128B-swizzled K-major tiles)
 //   warp 1 : MMA issuer     (one elected lane, tcgen05.mma cta_group::1, M=128,N=BLOCK_N,K=16)
 //   warp 2 : TMEM allocator (2 accumulator stages so the epilogue overlaps the next tile)
 //   warps 4-11: epilogue    (tcgen05.ld 32x32b -> registers -> fused math -> swizzled smem slab ->
@@ -187,20 +187,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_n_tiles = p.num_n_tiles;
 
-  if (warp == 0) {
-    // ========================= TMA producer =========================
-    // A single thread feeds the ring; the per-k-block path is kept free of divisions and
-    // parameter reloads (it was the bottleneck of the first version: ~680 cycles per k-block).
+  if (warp == 0 || warp == 3) {
+    // ========================= TMA producers (2 warps) =========================
+    // One thread of warp 0 feeds the even k-blocks of the ring, one thread of warp 3 the odd ones.
+    // A single producer thread costs ~500 issue cycles per k-block (measured) against 512 cycles of
+    // MMA work per 128x256x64 block, so one producer alone caps the kernel; the per-k-block path is
+    // also kept free of divisions and parameter reloads.
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t g = (warp == 0) ? 0u : 1u;   // parity toggle: handle a k-block when (g & 1) == 0
       const int a_mode = p.a_mode;
       const int nkb = p.num_k_blocks;
-      auto acquire = [&](uint8_t*& sa, uint64_t*& fb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        sa = smem + stage * L::kStageBytes;
-        fb = &full_bar[stage];
-        mbar_expect_tx(fb, L::kStageBytes);
+      auto acquire = [&](uint8_t*& sa, uint64_t*& fb) -> bool {
+        const bool mine = (g++ & 1u) == 0u;
+        if (mine) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          sa = smem + stage * L::kStageBytes;
+          fb = &full_bar[stage];
+          mbar_expect_tx(fb, L::kStageBytes);
+        }
+        return mine;
       };
       auto advance = [&]() {
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -211,9 +218,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
           for (int kb = 0; kb < nkb; ++kb) {
             uint8_t* sa; uint64_t* fb;
-            acquire(sa, fb);
-            tma_load_2d(sa, &tmap_a, fb, kb * BLOCK_K, m0);
-            tma_load_2d(sa + L::kABytes, &tmap_b, fb, kb * BLOCK_K, n0);
+            if (acquire(sa, fb)) {
+              tma_load_2d(sa, &tmap_a, fb, kb * BLOCK_K, m0);
+              tma_load_2d(sa + L::kABytes, &tmap_b, fb, kb * BLOCK_K, n0);
+            }
             advance();
           }
         }
@@ -234,17 +242,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               for (int kw_ = 0; kw_ < taps_w; ++kw_) {
                 for (int cb = 0; cb < cin_blocks; ++cb) {
                   uint8_t* sa; uint64_t* fb;
-                  acquire(sa, fb);
-                  uint8_t* s_act = SWAP ? sa + L::kABytes : sa;      // activation box
-                  uint8_t* s_wgt = SWAP ? sa : sa + L::kABytes;      // weight rows
-                  if (a_mode == 1) {
-                    tma_load_4d(s_act, &tmap_a, fb, cb * BLOCK_K, w0 + kw_ - pad_w, h0 + kh_ - pad_h, t_in);
-                  } else {
-                    // pair view (2C, W/2, 2, H/2, T): input pixel 2*o + k -> pair o + k/2, phase k%2
-                    tma_load_5d(s_act, &tmap_a, fb, (kw_ & 1) * cin + cb * BLOCK_K, w0 + (kw_ >> 1), kh_ & 1,
-                                h0 + (kh_ >> 1), t_in);
+                  if (acquire(sa, fb)) {
+                    uint8_t* s_act = SWAP ? sa + L::kABytes : sa;      // activation box
+                    uint8_t* s_wgt = SWAP ? sa : sa + L::kABytes;      // weight rows
+                    if (a_mode == 1) {
+                      tma_load_4d(s_act, &tmap_a, fb, cb * BLOCK_K, w0 + kw_ - pad_w, h0 + kh_ - pad_h, t_in);
+                    } else {
+                      // pair view (2C, W/2, 2, H/2, T): input pixel 2*o + k -> pair o + k/2, phase k%2
+                      tma_load_5d(s_act, &tmap_a, fb, (kw_ & 1) * cin + cb * BLOCK_K, w0 + (kw_ >> 1), kh_ & 1,
+                                  h0 + (kh_ >> 1), t_in);
+                    }
+                    tma_load_2d(s_wgt, &tmap_b, fb, kcol, n0);
                   }
-                  tma_load_2d(s_wgt, &tmap_b, fb, kcol, n0);
                   kcol += BLOCK_K;
                   advance();
                 }
