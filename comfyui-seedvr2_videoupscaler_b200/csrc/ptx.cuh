@@ -206,13 +206,20 @@ __device__ __forceinline__ float exp2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// silu(x) = x * sigmoid(x) = 0.5 x (1 + tanh(x / 2)): one MUFU op (tanh.approx) instead of ex2 + rcp
+__device__ __forceinline__ float silu_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   const float u = k0 * (x + k1 * x * x * x);
-  // tanh(u) = 1 - 2 / (1 + exp(2u))
-  const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
-  return 0.5f * x * (1.0f + t);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
