@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 #include "svr2_internal.h"
@@ -77,10 +78,10 @@ enum : int {
   EPI_PEXP = 512,     // out: bf16(exp2(acc*out_scale - rowvec[m]))                         (attention pass 2)
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TWO = false>
 struct SmemLayout {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kBBytes = (TWO ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;   // a CTA pair splits B along N
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = 8 * 4096;            // epilogue: 8 warps x (32 rows x 128 B)
   static constexpr int kBudget = 232448 - kStagingBytes - 256 - 1024;   // 227 KB max dynamic smem
@@ -143,11 +144,16 @@ __device__ __forceinline__ RowDest row_dest(const GemmParams& p, int m_blk, int 
 // SWAP (conv only, BLOCK_N = 256): operands exchanged so that M = 128 output channels (weights as A)
 // and N = 256 output pixels (activation box as B).  Cout = 128 layers then run 128x256 tiles instead of
 // 128x128 ones, whose SS-MMA shared-memory read rate (128 B/clk) caps them near 1 PFLOP/s.
-template <int BLOCK_N, int KIND, bool SWAP = false>
+// TWO: a cluster of 2 CTAs (one SM pair) works on a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2:
+// each CTA loads its own 128 A rows and half of the B rows, CTA 0 issues the MMAs for both, each CTA
+// drains its own 128 x BLOCK_N accumulator.  Halves the B traffic per SM and the per-SM smem read rate.
+template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
-  using L = SmemLayout<BLOCK_N>;
+  static_assert(!(SWAP && TWO), "swap-AB and CTA pairs are mutually exclusive");
+  using L = SmemLayout<BLOCK_N, TWO>;
+  const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
   constexpr int kStages = L::kStages;
   constexpr int ACC_STRIDE = BLOCK_N < 32 ? 32 : BLOCK_N;   // TMEM columns per accumulator stage
   constexpr uint32_t kTmemCols = (2 * ACC_STRIDE <= 64) ? 64 : (2 * ACC_STRIDE <= 128) ? 128
@@ -174,18 +180,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 256);
+      mbar_init(&tmem_empty[i], TWO ? 512 : 256);   // pair: the epilogue threads of both CTAs arrive at CTA 0
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
+  if constexpr (TWO) cluster_sync_all();            // barriers of both CTAs initialised before any remote arrive
+  if (warp == 2) {
+    if constexpr (TWO) tmem_alloc_2cta<kTmemCols>(tmem_slot);
+    else tmem_alloc<kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // tile schedule: 1-CTA: one 128-row m-tile per tile; pair: m-tiles (2j, 2j+1) per tile, same tile in both CTAs
   const int num_n_tiles = p.num_n_tiles;
+  const int num_tiles = (TWO ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * num_n_tiles;
+  const int tile0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 || warp == 3) {
     // ========================= TMA producers (2 warps) =========================
@@ -205,7 +218,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&empty_bar[stage], phase ^ 1);
           sa = smem + stage * L::kStageBytes;
           fb = &full_bar[stage];
-          mbar_expect_tx(fb, L::kStageBytes);
+          if constexpr (TWO) {
+            if (cta_rank == 0) mbar_expect_tx(fb, 2 * L::kStageBytes);   // bytes of both CTAs land on CTA 0's barrier
+          } else {
+            mbar_expect_tx(fb, L::kStageBytes);
+          }
         }
         return mine;
       };
@@ -213,14 +230,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       };
       if (a_mode == 0) {
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int m_blk = tile / num_n_tiles, n_blk = tile - m_blk * num_n_tiles;
-          const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+          const int m_sup = tile / num_n_tiles, n_blk = tile - m_sup * num_n_tiles;
+          const int m_blk = TWO ? 2 * m_sup + (int)cta_rank : m_sup;
+          const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N + (TWO ? (int)cta_rank * (BLOCK_N / 2) : 0);
           for (int kb = 0; kb < nkb; ++kb) {
             uint8_t* sa; uint64_t* fb;
             if (acquire(sa, fb)) {
-              tma_load_2d(sa, &tmap_a, fb, kb * BLOCK_K, m0);
-              tma_load_2d(sa + L::kABytes, &tmap_b, fb, kb * BLOCK_K, n0);
+              if constexpr (TWO) {
+                tma2_load_2d(sa, &tmap_a, fb, kb * BLOCK_K, m0);
+                tma2_load_2d(sa + L::kABytes, &tmap_b, fb, kb * BLOCK_K, n0);
+              } else {
+                tma_load_2d(sa, &tmap_a, fb, kb * BLOCK_K, m0);
+                tma_load_2d(sa + L::kABytes, &tmap_b, fb, kb * BLOCK_K, n0);
+              }
             }
             advance();
           }
@@ -229,12 +252,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int per_frame = p.tiles_w * p.tiles_h, tiles_w = p.tiles_w;
         const int bw = p.bw, bh = p.bh, pad_h = p.pad_h, pad_w = p.pad_w, stride_t = p.stride_t;
         const int taps_t = p.taps_t, taps_h = p.taps_h, taps_w = p.taps_w, cin_blocks = p.cin_blocks, cin = p.cin;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int m_blk = tile / num_n_tiles, n_blk = tile - m_blk * num_n_tiles;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+          const int m_sup = tile / num_n_tiles, n_blk = tile - m_sup * num_n_tiles;
+          const int m_blk = TWO ? 2 * m_sup + (int)cta_rank : m_sup;
           const int t_o = m_blk / per_frame, r = m_blk - t_o * per_frame;
           const int th = r / tiles_w;
           const int h0 = th * bh, w0 = (r - th * tiles_w) * bw;
-          const int n0 = n_blk * (SWAP ? BLOCK_M : BLOCK_N);
+          const int n0 = n_blk * (SWAP ? BLOCK_M : BLOCK_N) + (TWO ? (int)cta_rank * (BLOCK_N / 2) : 0);
           int kcol = 0;
           for (int kt_ = 0; kt_ < taps_t; ++kt_) {
             const int t_in = t_o * stride_t + kt_;
@@ -245,14 +269,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   if (acquire(sa, fb)) {
                     uint8_t* s_act = SWAP ? sa + L::kABytes : sa;      // activation box
                     uint8_t* s_wgt = SWAP ? sa : sa + L::kABytes;      // weight rows
-                    if (a_mode == 1) {
-                      tma_load_4d(s_act, &tmap_a, fb, cb * BLOCK_K, w0 + kw_ - pad_w, h0 + kh_ - pad_h, t_in);
+                    if constexpr (TWO) {
+                      if (a_mode == 1) {
+                        tma2_load_4d(s_act, &tmap_a, fb, cb * BLOCK_K, w0 + kw_ - pad_w, h0 + kh_ - pad_h, t_in);
+                      } else {
+                        tma2_load_5d(s_act, &tmap_a, fb, (kw_ & 1) * cin + cb * BLOCK_K, w0 + (kw_ >> 1), kh_ & 1,
+                                     h0 + (kh_ >> 1), t_in);
+                      }
+                      tma2_load_2d(s_wgt, &tmap_b, fb, kcol, n0);
                     } else {
-                      // pair view (2C, W/2, 2, H/2, T): input pixel 2*o + k -> pair o + k/2, phase k%2
-                      tma_load_5d(s_act, &tmap_a, fb, (kw_ & 1) * cin + cb * BLOCK_K, w0 + (kw_ >> 1), kh_ & 1,
-                                  h0 + (kh_ >> 1), t_in);
+                      if (a_mode == 1) {
+                        tma_load_4d(s_act, &tmap_a, fb, cb * BLOCK_K, w0 + kw_ - pad_w, h0 + kh_ - pad_h, t_in);
+                      } else {
+                        // pair view (2C, W/2, 2, H/2, T): input pixel 2*o + k -> pair o + k/2, phase k%2
+                        tma_load_5d(s_act, &tmap_a, fb, (kw_ & 1) * cin + cb * BLOCK_K, w0 + (kw_ >> 1), kh_ & 1,
+                                    h0 + (kh_ >> 1), t_in);
+                      }
+                      tma_load_2d(s_wgt, &tmap_b, fb, kcol, n0);
                     }
-                    tma_load_2d(s_wgt, &tmap_b, fb, kcol, n0);
                   }
                   kcol += BLOCK_K;
                   advance();
@@ -265,14 +299,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     // ========================= MMA issuer =========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TWO ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
       const int nkb = p.num_k_blocks;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
@@ -285,12 +319,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in the >>4 address field
-            umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0);
+            if constexpr (TWO) umma_bf16_2cta(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) once the MMAs have read it
+          if constexpr (TWO) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);      // accumulator complete
+        if constexpr (TWO) umma_commit_2cta(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);   // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -310,6 +346,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     constexpr int ROWS_PER_IT = 32 / CPR;
     constexpr int N_IT = 32 / ROWS_PER_IT;                                // warp-wide accesses per phase
     constexpr int kBatch = N_IT < 4 ? N_IT : 4;
+    auto tmem_empty_arrive = [&](uint64_t* bar) {
+      if constexpr (TWO) mbar_arrive_cta0(bar); else mbar_arrive(bar);
+    };
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
     const int half = (warp - 4) >> 2;     // which half of the columns
     const int row = q * 32 + lane;        // tile row owned by this thread
@@ -323,8 +362,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const __nv_bfloat16* __restrict__ resid = p.residual;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n_tiles, n_blk = tile - m_blk * num_n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m_sup = tile / num_n_tiles, n_blk = tile - m_sup * num_n_tiles;
+      const int m_blk = TWO ? 2 * m_sup + (int)cta_rank : m_sup;
       if constexpr (SWAP) {
         // accumulator lanes = output channels (this thread: co), columns = the tile's 256 pixels.
         const int per_frame = p.tiles_w * p.tiles_h;
@@ -346,7 +386,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_wait();
           if (c0 + 32 >= half * 128 + 128) {
             tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
+            tmem_empty_arrive(&tmem_empty[acc]);
           }
           // transpose through the slab: row = pixel (128 B stride), 32 channels (64 B) per row
 #pragma unroll
@@ -392,7 +432,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
-      const RowDest dst = row_dest<BLOCK_N>(p, m_blk, n_blk, row, N_COLS);
+      RowDest dst = row_dest<BLOCK_N>(p, m_blk, n_blk, row, N_COLS);
+      if (TWO && m_blk >= p.num_m_tiles) { dst.valid = 0; dst.dup = 0; }
       const int n_base = n_blk * (KIND == KIND_SWIGLU ? BLOCK_N / 2 : BLOCK_N);   // first output column
 
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -433,7 +474,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        tmem_empty_arrive(&tmem_empty[acc]);
         const int m = m_blk * BLOCK_M + row;
         if (active && m < p.M) {
           const int slot = (N_COLS >= 64) ? n_blk * 2 + half : n_blk;
@@ -441,7 +482,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       } else if (!active) {
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        tmem_empty_arrive(&tmem_empty[acc]);
       } else {
 #pragma unroll 1
         for (int ph0 = col_lo; ph0 < col_lo + COLS_W; ph0 += PH_COLS) {
@@ -531,7 +572,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           if (ph0 + PH_COLS >= col_lo + COLS_W) {   // all TMEM reads of this warp are done for this tile
             tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
+            tmem_empty_arrive(&tmem_empty[acc]);
           }
           __syncwarp();
           // ---------------- phase 2 ----------------
@@ -590,9 +631,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();     // the peer may still be arriving on / reading from this CTA
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (TWO) tmem_dealloc_2cta<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -652,27 +695,71 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BLOCK_N, int KIND, bool SWAP = false>
+template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N>;
+  using L = SmemLayout<BLOCK_N, TWO>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, KIND, SWAP, TWO>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, KIND, SWAP>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
     configured = true;
   }
-  int tiles = p.num_m_tiles * p.num_n_tiles;
-  int grid = tiles < num_sms() ? tiles : num_sms();
-  if (grid <= 0) return SVR2_OK;
-  gemm_tcgen05_kernel<BLOCK_N, KIND, SWAP><<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
-  return SVR2_OK;
+  if constexpr (TWO) {
+    const int tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    int clusters = num_sms() / 2;
+    if (tiles < clusters) clusters = tiles;
+    if (clusters <= 0) return SVR2_OK;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
+    return SVR2_OK;
+  } else {
+    int tiles = p.num_m_tiles * p.num_n_tiles;
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    if (grid <= 0) return SVR2_OK;
+    kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
+    return SVR2_OK;
+  }
+}
+
+// 0 = single-CTA tiles, 1 = CTA pairs (cta_group::2) for the 256/128-column kernels; SVR2_CTA_PAIR overrides
+static int g_pair_mode = -1;
+static int pair_mode() {
+  if (g_pair_mode < 0) {
+    const char* e = getenv("SVR2_CTA_PAIR");
+    g_pair_mode = e ? atoi(e) : 1;   // default: CTA pairs for the 256-column kernels (+9..14 % measured)
+  }
+  return g_pair_mode;
+}
+extern "C" void svr2_set_cta_pair(int on) { g_pair_mode = on ? 1 : 0; }
+
+// pair tiles are used for the 256/128-column bf16 / SwiGLU kernels when there are at least two m-tiles
+static bool want_pair(int block_n, int epi, int num_m_tiles) {
+  if (!pair_mode() || num_m_tiles < 2) return false;
+  if (epi & (EPI_F32 | EPI_ROWSTAT | EPI_PEXP)) return false;
+  return block_n == 256;   // 128-column pair tiles lose to swap-AB (855-1042 vs ~1400 TFLOP/s measured)
 }
 
 static int dispatch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                         cudaStream_t s) {
+                         cudaStream_t s, bool pair = false) {
+  if (pair) {
+    if (p.epi & EPI_SWIGLU) return launch_gemm<256, KIND_SWIGLU, false, true>(ta, tb, p, s);
+    return launch_gemm<256, KIND_BF16, false, true>(ta, tb, p, s);
+  }
   if (p.epi & EPI_SWIGLU) {
     if (block_n == 256) return launch_gemm<256, KIND_SWIGLU>(ta, tb, p, s);
     return set_error(SVR2_ERR_ARG, "SwiGLU epilogue needs BLOCK_N = 256");
@@ -740,8 +827,9 @@ extern "C" int svr2_linear_bf16(const void* a, int64_t lda, const void* w, int64
   uint32_t ba[2] = {BLOCK_K, BLOCK_M};
   int rc = make_tmap_bf16(&ta, a, 2, da, sa, ba);
   if (rc) return rc;
+  const bool pair = want_pair(bn, epi_flags, (M + BLOCK_M - 1) / BLOCK_M);
   uint64_t db[2] = {(uint64_t)K, (uint64_t)N}, sb[1] = {(uint64_t)ldw * 2};
-  uint32_t bb[2] = {BLOCK_K, (uint32_t)bn};
+  uint32_t bb[2] = {BLOCK_K, (uint32_t)(pair ? bn / 2 : bn)};
   rc = make_tmap_bf16(&tb, w, 2, db, sb, bb);
   if (rc) return rc;
   GemmParams p{};
@@ -762,7 +850,7 @@ extern "C" int svr2_linear_bf16(const void* a, int64_t lda, const void* w, int64
   if (rowstat && ldc < (int64_t)p.num_n_tiles * (bn >= 64 ? 2 : 1))
     return set_error(SVR2_ERR_ARG, "EPI_ROWSTAT: ldc (float2 slots per row) must be >= svr2_rowstat_slots(N)");
   if ((p.epi & EPI_RESIDUAL) && !residual) return set_error(SVR2_ERR_ARG, "EPI_RESIDUAL without residual");
-  return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream);
+  return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream, pair);
 }
 
 // number of (max, sum) float2 partial slots per row that EPI_ROWSTAT writes for a given N
@@ -811,8 +899,10 @@ extern "C" int svr2_conv3d_bf16(const void* x, int T_in_total, int H, int W, int
   }
   if (rc) return rc;
   const int K = kt * kh * kw * Cin;
+  const int n_m_tiles = T_out * ((W_out + bw - 1) / bw) * ((H_out + bh - 1) / bh);
+  const bool pair = !swap && want_pair(bn, 0, n_m_tiles);
   uint64_t db[2] = {(uint64_t)K, (uint64_t)Cout}, sb[1] = {(uint64_t)K * 2};
-  uint32_t bb[2] = {BLOCK_K, (uint32_t)bn};
+  uint32_t bb[2] = {BLOCK_K, (uint32_t)(pair ? bn / 2 : bn)};
   rc = make_tmap_bf16(&tb, w, 2, db, sb, bb);
   if (rc) return rc;
   GemmParams p{};
@@ -839,7 +929,7 @@ extern "C" int svr2_conv3d_bf16(const void* x, int T_in_total, int H, int W, int
   p.residual = (const __nv_bfloat16*)residual;
   p.out = y;
   if (swap) return launch_gemm<256, KIND_BF16, true>(ta, tb, p, (cudaStream_t)stream);
-  return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream);
+  return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream, pair);
 }
 
 // Upsample3D: 1x1x1 conv (GEMM over voxels) with the 3-D pixel shuffle fused into the store.
@@ -856,8 +946,9 @@ extern "C" int svr2_upsample_shuffle_bf16(const void* x, int F, int H, int W, in
   uint32_t ba[2] = {BLOCK_K, BLOCK_M};
   int rc = make_tmap_bf16(&ta, x, 2, da, sa, ba);
   if (rc) return rc;
+  const bool pair = want_pair(bn, 0, (M + BLOCK_M - 1) / BLOCK_M);
   uint64_t db[2] = {(uint64_t)C, (uint64_t)N}, sb[1] = {(uint64_t)C * 2};
-  uint32_t bb[2] = {BLOCK_K, (uint32_t)bn};
+  uint32_t bb[2] = {BLOCK_K, (uint32_t)(pair ? bn / 2 : bn)};
   rc = make_tmap_bf16(&tb, w, 2, db, sb, bb);
   if (rc) return rc;
   GemmParams p{};
@@ -875,5 +966,5 @@ extern "C" int svr2_upsample_shuffle_bf16(const void* x, int F, int H, int W, in
   p.shuf_drop = (temporal && drop_head) ? 1 : 0;
   p.bias = (const __nv_bfloat16*)bias;
   p.out = y;
-  return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream);
+  return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream, pair);
 }

@@ -21,6 +21,7 @@ EPI_ROWSTAT, EPI_PEXP = 256, 512
 _P = c_void_p
 SIGNATURES = {
     "svr2_version": [],
+    "svr2_set_cta_pair": [c_int],
     "svr2_device_check": [POINTER(c_int), POINTER(c_int), POINTER(c_int)],
     "svr2_linear_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, c_float, _P],
     "svr2_conv3d_bf16": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -62,7 +63,7 @@ def load() -> ctypes.CDLL:
         lib.svr2_last_error.argtypes = []
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
-            fn.restype = c_int64 if name.endswith("_bytes") else c_int
+            fn.restype = c_int64 if name.endswith("_bytes") else (None if name == "svr2_set_cta_pair" else c_int)
             fn.argtypes = args
         _lib = lib
     return _lib

@@ -41,6 +41,9 @@ enum svr2_epilogue {
 };
 
 const char* svr2_last_error(void);
+/* 1: GEMM/conv tiles are executed by CTA pairs (tcgen05 cta_group::2, 256-row tiles); 0: single-CTA tiles.
+ * Default from the environment variable SVR2_CTA_PAIR (unset = library default). */
+void svr2_set_cta_pair(int on);
 int svr2_version(void);
 /* fills sm count / major / minor of the current device; SVR2_ERR_ARCH unless sm_100 */
 int svr2_device_check(int* sm_count, int* cc_major, int* cc_minor);
