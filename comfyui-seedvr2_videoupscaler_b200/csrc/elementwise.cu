@@ -315,6 +315,55 @@ __global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const double* _
   }
 }
 
+// finalize from conv-epilogue partials: part [frames][slots][C/8] (sum0, sq0, sum1, sq1) per channel octet
+// (x/y: channels 0-3 of the octet, z/w: channels 4-7).  One block per (group, frame); every thread sums a
+// fixed strided subset of the slots in double, then a fixed-order shared-memory tree -> deterministic.
+__global__ void __launch_bounds__(256) groupnorm_finalize_fused_kernel(const float4* __restrict__ part, int slots,
+                                                                       int hw, int C,
+                                                                       const __nv_bfloat16* __restrict__ gamma,
+                                                                       const __nv_bfloat16* __restrict__ beta,
+                                                                       float eps, float2* __restrict__ coef) {
+  __shared__ double sh_s[256], sh_q[256];
+  const int g = blockIdx.x, f = blockIdx.y, cpg = C / 32, noct = C / 8;
+  double ds = 0.0, dq = 0.0;
+  const float4* base = part + (long long)f * slots * noct;
+  if (cpg == 4) {
+    const int o = g >> 1, hi = g & 1;
+    for (int sl = threadIdx.x; sl < slots; sl += 256) {
+      const float4 v = base[(long long)sl * noct + o];
+      ds += hi ? v.z : v.x;
+      dq += hi ? v.w : v.y;
+    }
+  } else {
+    const int no = cpg / 8;
+    for (int sl = threadIdx.x; sl < slots; sl += 256) {
+      for (int o = g * no; o < (g + 1) * no; ++o) {
+        const float4 v = base[(long long)sl * noct + o];
+        ds += (double)v.x + (double)v.z;
+        dq += (double)v.y + (double)v.w;
+      }
+    }
+  }
+  sh_s[threadIdx.x] = ds;
+  sh_q[threadIdx.x] = dq;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      sh_s[threadIdx.x] += sh_s[threadIdx.x + st];
+      sh_q[threadIdx.x] += sh_q[threadIdx.x + st];
+    }
+    __syncthreads();
+  }
+  const double n = (double)hw * cpg;
+  const double mean = sh_s[0] / n, var = sh_q[0] / n - mean * mean;
+  const float rstd = rsqrtf(fmaxf((float)var, 0.f) + eps);
+  if (threadIdx.x < cpg) {
+    const int c = g * cpg + threadIdx.x;
+    const float a = rstd * __bfloat162float(gamma[c]);
+    coef[(long long)f * C + c] = make_float2(a, __bfloat162float(beta[c]) - (float)mean * a);
+  }
+}
+
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x,
                                                               __nv_bfloat16* __restrict__ y, int hw, int C, int silu,
                                                               int out_t_pad, int out_dup_head,
@@ -585,6 +634,29 @@ extern "C" int svr2_groupnorm_bf16(const void* x, void* y, int frames, int hw, i
   groupnorm_finalize_kernel<<<frames, 256, 0, s>>>(scratch, blocks_x, hw, C, (const __nv_bfloat16*)gamma,
                                                    (const __nv_bfloat16*)beta, eps, coef);
   rc = check_launch("groupnorm_finalize");
+  if (rc) return rc;
+  const long long nvec = (long long)hw * C / 8;
+  int bx = (int)((nvec + 256 * 8 - 1) / (256 * 8));
+  if (bx < 1) bx = 1;
+  groupnorm_apply_kernel<<<dim3(bx, frames), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, C, silu,
+                                                          out_t_pad, out_dup_head, coef);
+  return check_launch("groupnorm_apply");
+}
+
+// GroupNorm(+SiLU) whose statistics were produced by svr2_conv3d_stats_bf16: finalize + apply only
+// (saves the separate statistics read pass).  coef_scratch: frames * C * 8 bytes.
+extern "C" int svr2_groupnorm_from_stats_bf16(const void* x, void* y, int frames, int hw, int C, const void* gamma,
+                                              const void* beta, float eps, int silu, int out_t_pad, int out_dup_head,
+                                              const void* stat_partial, int stat_slots, void* coef_scratch,
+                                              void* stream) {
+  if (C % 32 || (C / 32 != 4 && C / 32 != 8 && C / 32 != 16))
+    return set_error(SVR2_ERR_ARG, "groupnorm: C must be 128, 256 or 512");
+  cudaStream_t s = (cudaStream_t)stream;
+  float2* coef = (float2*)coef_scratch;
+  groupnorm_finalize_fused_kernel<<<dim3(32, frames), 256, 0, s>>>((const float4*)stat_partial, stat_slots, hw, C,
+                                                         (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, eps,
+                                                         coef);
+  int rc = check_launch("groupnorm_finalize_fused");
   if (rc) return rc;
   const long long nvec = (long long)hw * C / 8;
   int bx = (int)((nvec + 256 * 8 - 1) / (256 * 8));

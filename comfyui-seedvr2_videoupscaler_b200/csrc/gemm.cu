@@ -63,6 +63,8 @@ struct GemmParams {
   const float* gate;              // [N] or null
   const __nv_bfloat16* residual;  // same layout as out, or null
   void* out;
+  float4* stat_partial;           // conv only: [frame][slot][N/8] (sum0, sq0, sum1, sq1) of the stored values, or null
+  int stat_slots;                 // slots per frame (tiles per frame x warps covering distinct rows)
 };
 
 enum : int {
@@ -90,6 +92,17 @@ struct SmemLayout {
   static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
+
+// per-lane GroupNorm partial sums of the 8 bf16 values a lane stores (channels 0-3 -> x/y, 4-7 -> z/w)
+__device__ __forceinline__ void stat_acc(float4& a, const uint4& d) {
+  const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+    if (e < 2) { a.x += lo + hi; a.y += lo * lo + hi * hi; }
+    else { a.z += lo + hi; a.w += lo * lo + hi * hi; }
+  }
+}
 
 enum : int { KIND_BF16 = 0, KIND_SWIGLU = 1, KIND_F32 = 2, KIND_ROWSTAT = 3, KIND_PEXP = 4 };
 
@@ -379,6 +392,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_STRIDE;
         unsigned short* slab16 = reinterpret_cast<unsigned short*>(slab);
+        float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
         for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
           uint32_t v[32];
@@ -422,12 +436,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               d = make_uint4(o[0], o[1], o[2], o[3]);
             }
             *reinterpret_cast<uint4*>(ob + off[i]) = d;
+            if (p.stat_partial) stat_acc(st, d);
             if (flags[i] & 2) {
               *reinterpret_cast<uint4*>(ob + off[i] - p.out_frame_stride) = d;
               *reinterpret_cast<uint4*>(ob + off[i] - 2 * p.out_frame_stride) = d;
             }
           }
           __syncwarp();
+        }
+        if (p.stat_partial) {
+          // lanes with the same channel octet (lane & 3) hold different pixels: fixed-order xor tree
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            st.x += __shfl_xor_sync(0xffffffffu, st.x, o); st.y += __shfl_xor_sync(0xffffffffu, st.y, o);
+            st.z += __shfl_xor_sync(0xffffffffu, st.z, o); st.w += __shfl_xor_sync(0xffffffffu, st.w, o);
+          }
+          if (lane < 4 && t_o < p.T_out) {
+            const int octet = (n_blk * BLOCK_M + q * 32) / 8 + lane;
+            if (octet * 8 < p.N)
+              p.stat_partial[((long long)t_o * p.stat_slots + r * 2 + half) * (p.N / 8) + octet] = st;
+          }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
@@ -579,6 +607,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int ch = lane % CPR, rsub = lane / CPR;
           const int col = ph0 + (KIND == KIND_F32 ? ch * 4 : ch * 8);
           const bool col_ok = (n_base + col) < n_lim;
+          float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
           for (int b0 = 0; b0 < N_IT; b0 += kBatch) {
             long long off[kBatch];
@@ -615,11 +644,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   }
                 }
                 *reinterpret_cast<uint4*>(ob + off[i] + col) = d;
+                if constexpr (KIND == KIND_BF16) {
+                  if (p.stat_partial) stat_acc(st, d);
+                }
                 if (flags[i] & 2) {
                   *reinterpret_cast<uint4*>(ob + off[i] - p.out_frame_stride + col) = d;
                   *reinterpret_cast<uint4*>(ob + off[i] - 2 * p.out_frame_stride + col) = d;
                 }
               }
+            }
+          }
+          if constexpr (KIND == KIND_BF16) {
+            if (p.stat_partial && p.a_mode != 0) {
+              // lanes with equal (lane % CPR) own the same channel octet for different rows
+#pragma unroll
+              for (int o = CPR; o < 32; o <<= 1) {
+                st.x += __shfl_xor_sync(0xffffffffu, st.x, o); st.y += __shfl_xor_sync(0xffffffffu, st.y, o);
+                st.z += __shfl_xor_sync(0xffffffffu, st.z, o); st.w += __shfl_xor_sync(0xffffffffu, st.w, o);
+              }
+              const int per_frame = p.tiles_w * p.tiles_h;
+              const int t_o = m_blk / per_frame, rt = m_blk - t_o * per_frame;
+              if (lane < CPR && col_ok && m_blk < p.num_m_tiles)
+                p.stat_partial[((long long)t_o * p.stat_slots + rt * 4 + q) * (p.N / 8) + (n_base + col) / 8] = st;
             }
           }
           __syncwarp();
@@ -862,10 +908,36 @@ extern "C" int svr2_rowstat_slots(int N) {
 // Causal Conv3d as implicit GEMM.  x: NDHWC bf16 with `in_t_pad` halo frames in front
 // (frames [0,in_t_pad) hold the causal context; the first real frame is at index in_t_pad).
 // w: [Cout][kt][kh][kw][Cin] bf16 (K-major).  y: NDHWC bf16 with out_t_pad halo frames.
+static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout, int kt,
+                       int kh, int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags,
+                       const void* bias, const void* residual, void* y, int out_t_pad, int out_dup_head,
+                       int ldc, void* stat_partial, int64_t stat_bytes, int* stat_slots_out, void* stream);
+
 extern "C" int svr2_conv3d_bf16(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout, int kt,
                                 int kh, int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags,
                                 const void* bias, const void* residual, void* y, int out_t_pad, int out_dup_head,
                                 int ldc, void* stream) {
+  return conv3d_impl(x, T_in_total, H, W, Cin, w, Cout, kt, kh, kw, stride_t, stride_hw, pad_hw, T_out, epi_flags, bias,
+                     residual, y, out_t_pad, out_dup_head, ldc, nullptr, 0, nullptr, stream);
+}
+
+// Same conv, additionally emitting per-tile GroupNorm partial sums of the stored output
+// (stat_partial: [T_out][slots][Cout/8] float4, slots returned in *stat_slots; see svr2_groupnorm_from_stats_bf16).
+// Call with stat_partial == NULL to query *stat_slots / the required bytes (= T_out * slots * Cout/8 * 16).
+extern "C" int svr2_conv3d_stats_bf16(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout,
+                                      int kt, int kh, int kw, int stride_t, int stride_hw, int pad_hw, int T_out,
+                                      int epi_flags, const void* bias, const void* residual, void* y, int out_t_pad,
+                                      int out_dup_head, int ldc, void* stat_partial, int64_t stat_bytes,
+                                      int* stat_slots, void* stream) {
+  if (!stat_slots) return set_error(SVR2_ERR_ARG, "svr2_conv3d_stats_bf16: stat_slots must not be NULL");
+  return conv3d_impl(x, T_in_total, H, W, Cin, w, Cout, kt, kh, kw, stride_t, stride_hw, pad_hw, T_out, epi_flags, bias,
+                     residual, y, out_t_pad, out_dup_head, ldc, stat_partial, stat_bytes, stat_slots, stream);
+}
+
+static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout, int kt,
+                       int kh, int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags,
+                       const void* bias, const void* residual, void* y, int out_t_pad, int out_dup_head,
+                       int ldc, void* stat_partial, int64_t stat_bytes, int* stat_slots_out, void* stream) {
   if (Cin % 64) return set_error(SVR2_ERR_ARG, "svr2_conv3d_bf16: Cin must be a multiple of 64 (pad channels)");
   if (Cout % 8 || ldc % 8) return set_error(SVR2_ERR_ARG, "svr2_conv3d_bf16: Cout/ldc must be multiples of 8");
   if (stride_hw != 1 && stride_hw != 2) return set_error(SVR2_ERR_ARG, "stride_hw must be 1 or 2");
@@ -928,6 +1000,16 @@ extern "C" int svr2_conv3d_bf16(const void* x, int T_in_total, int H, int W, int
   p.bias = (const __nv_bfloat16*)bias;
   p.residual = (const __nv_bfloat16*)residual;
   p.out = y;
+  if (stat_slots_out) {
+    if (Cout % 8 || ldc != Cout) return set_error(SVR2_ERR_ARG, "conv stats: need Cout % 8 == 0 and ldc == Cout");
+    const int slots = p.tiles_w * p.tiles_h * (swap ? 2 : 4);
+    *stat_slots_out = slots;
+    if (!stat_partial) return SVR2_OK;   // size query only
+    const int64_t need = (int64_t)T_out * slots * (Cout / 8) * 16;
+    if (stat_bytes < need) return set_error(SVR2_ERR_ARG, "conv stats: stat_partial buffer too small");
+    p.stat_partial = (float4*)stat_partial;
+    p.stat_slots = slots;
+  }
   if (swap) return launch_gemm<256, KIND_BF16, true>(ta, tb, p, (cudaStream_t)stream);
   return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream, pair);
 }

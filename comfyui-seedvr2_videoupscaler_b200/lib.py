@@ -26,6 +26,10 @@ SIGNATURES = {
     "svr2_linear_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, c_float, _P],
     "svr2_conv3d_bf16": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_int, _P, _P, _P, c_int, c_int, c_int, _P],
+    "svr2_conv3d_stats_bf16": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                               c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, POINTER(c_int), _P],
+    "svr2_groupnorm_from_stats_bf16": [_P, _P, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, c_int, _P, c_int, _P,
+                                       _P],
     "svr2_upsample_shuffle_bf16": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_int, c_int, _P],
     "svr2_attn_varlen_bf16": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
     "svr2_rmsnorm_ada_bf16": [_P, _P, c_int, c_int, c_float, _P, _P, _P, c_int, _P],
@@ -83,7 +87,7 @@ def stream():
 
 
 # kernels launched per C-ABI call (for the bench's gpu_launches count)
-KERNELS_PER_CALL = {"svr2_groupnorm_bf16": 3}
+KERNELS_PER_CALL = {"svr2_groupnorm_bf16": 3, "svr2_groupnorm_from_stats_bf16": 2}
 
 
 class Profiler:

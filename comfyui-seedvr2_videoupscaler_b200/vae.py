@@ -32,6 +32,7 @@ class Act:
     def __init__(self, T, H, W, C, pad, device, buf=None):
         self.T, self.H, self.W, self.C, self.pad = T, H, W, C, pad
         self.buf = buf if buf is not None else torch.empty(pad + T, H, W, C, device=device, dtype=torch.bfloat16)
+        self.stats = None     # (partial sums tensor, slots) written by the producing conv's epilogue
 
     def without_halo(self):
         return self if self.pad == 0 else Act(self.T, self.H, self.W, self.C, 0, None, buf=self.body)
@@ -121,6 +122,14 @@ class B200VideoVAE:
     # ---- primitive wrappers ----------------------------------------------
     def _gn(self, x: Act, prefix: str, silu: bool, pad: int) -> Act:
         y = Act(x.T, x.H, x.W, x.C, pad, self.device)
+        if x.stats is not None:     # statistics came out of the producing conv's epilogue: finalize + apply only
+            part, slots = x.stats
+            coef = torch.empty(x.T * x.C * 2, device=self.device, dtype=torch.float32)
+            lib.call("svr2_groupnorm_from_stats_bf16", c_void_p(x.body_ptr()), lib.ptr(y.buf), x.T, x.H * x.W, x.C,
+                     lib.ptr(self.W[prefix + ".weight"]), lib.ptr(self.W[prefix + ".bias"]), 1e-6, int(silu), pad,
+                     int(pad > 0), lib.ptr(part), slots, lib.ptr(coef), lib.stream(),
+                     nbytes=4.0 * x.T * x.H * x.W * x.C)
+            return y
         need = lib.load().svr2_groupnorm_scratch_bytes(x.T, x.H * x.W, x.C)
         if self._stats is None or self._stats.numel() * 8 < need:
             self._stats = torch.empty((need + 7) // 8 + 1024, device=self.device, dtype=torch.float64)
@@ -131,7 +140,7 @@ class B200VideoVAE:
         return y
 
     def _conv(self, x: Act, prefix: str, *, out_pad=0, residual: Optional[Act] = None, stride_t=1, stride_hw=1,
-              cout=None, cin=None) -> Act:
+              cout=None, cin=None, stats=False) -> Act:
         w = self.W[prefix + ".weight"]
         kt, kh, kw = self.W[prefix + ".weight.k"]
         Cout = cout if cout is not None else w.shape[0]
@@ -147,9 +156,20 @@ class B200VideoVAE:
             res_ptr = c_void_p(residual.body_ptr() - out_pad * y.frame_elems * 2)
         epi = lib.EPI_BIAS | (lib.EPI_RESIDUAL if residual is not None else 0)
         pad_hw = 1 if (stride_hw == 1 and kh == 3) else 0
-        lib.call("svr2_conv3d_bf16", lib.ptr(x.buf), x.pad + x.T, x.H, x.W, Cin, lib.ptr(w), w.shape[0], kt, kh, kw,
-                 stride_t, stride_hw, pad_hw, T_out, epi, lib.ptr(self.W[prefix + ".bias"]), res_ptr, lib.ptr(y.buf),
-                 out_pad, int(out_pad > 0), w.shape[0], lib.stream(),
+        args = (lib.ptr(x.buf), x.pad + x.T, x.H, x.W, Cin, lib.ptr(w), w.shape[0], kt, kh, kw, stride_t, stride_hw,
+                pad_hw, T_out, epi, lib.ptr(self.W[prefix + ".bias"]), res_ptr, lib.ptr(y.buf), out_pad,
+                int(out_pad > 0), w.shape[0])
+        name, extra = "svr2_conv3d_bf16", ()
+        if stats and w.shape[0] in (128, 256, 512):
+            import ctypes
+            slots = ctypes.c_int(0)
+            rc = lib.load().svr2_conv3d_stats_bf16(*args, None, 0, ctypes.byref(slots), lib.stream())   # size query
+            if rc:
+                raise lib.Svr2Error(f"svr2_conv3d_stats_bf16 query failed ({rc}): {lib.load().svr2_last_error().decode()}")
+            part = torch.empty(T_out * slots.value * (w.shape[0] // 8) * 4, device=self.device, dtype=torch.float32)
+            y.stats = (part, slots.value)
+            name, extra = "svr2_conv3d_stats_bf16", (lib.ptr(part), part.numel() * 4, ctypes.byref(slots))
+        lib.call(name, *args, *extra, lib.stream(),
                  flops=2.0 * T_out * Ho * Wo * self.W[prefix + ".weight.real"][0] * kt * kh * kw
                  * self.W[prefix + ".weight.real"][1],
                  tag=(f"|{Cin}>{w.shape[0]}|k{kt}{kh}{kw}|s{stride_t}{stride_hw}|{T_out}x{Ho}x{Wo}"
@@ -159,13 +179,13 @@ class B200VideoVAE:
     def _resnet(self, x: Act, p: str, out_pad=0) -> Act:
         """ResnetBlock3D.forward (attn_video_vae.py:311-362)."""
         h = self._gn(x, p + "norm1", True, 2)
-        h = self._conv(h, p + "conv1")
+        h = self._conv(h, p + "conv1", stats=True)
         h = self._gn(h, p + "norm2", True, 2)
         if (p + "conv_shortcut.weight") in self.W:
             sc = self._conv(x.without_halo(), p + "conv_shortcut")
         else:
             sc = x
-        return self._conv(h, p + "conv2", out_pad=out_pad, residual=sc)
+        return self._conv(h, p + "conv2", out_pad=out_pad, residual=sc, stats=True)
 
     def _attention(self, x: Act, p: str) -> Act:
         """UNetMidBlock3D per-frame attention (attn_video_vae.py:656-668): GN -> q,k,v -> 1-head
@@ -227,7 +247,7 @@ class B200VideoVAE:
         lib.call("svr2_upsample_shuffle_bf16", c_void_p(x.body_ptr()), x.T, x.H, x.W, x.C,
                  lib.ptr(self.W[p + "upscale_conv.weight"]), lib.ptr(self.W[p + "upscale_conv.bias"]), int(temporal), 1,
                  lib.ptr(y.buf), 2, 1, lib.stream(), flops=2.0 * x.T * x.H * x.W * x.C * 4 * z * x.C)
-        return self._conv(y, p + "conv")
+        return self._conv(y, p + "conv", stats=True)
 
     # ---- public API --------------------------------------------------------
     @torch.no_grad()
@@ -245,7 +265,7 @@ class B200VideoVAE:
         dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[zin.dtype]
         x = Act(T, h, w, 64, 2, dev)
         lib.call("svr2_ncdhw_to_ndhwc_bf16", lib.ptr(zin), dt, 16, T, h, w, lib.ptr(x.buf), 64, 2, 1.0, lib.stream())
-        x = self._conv(x, "decoder.conv_in")
+        x = self._conv(x, "decoder.conv_in", stats=True)
         x = self._mid(x, "decoder.mid_block.")
         for i in range(4):
             for j in range(3):
@@ -288,7 +308,7 @@ class B200VideoVAE:
             h = self._resnet(h, p + "resnets.0.")
             h = self._resnet(h, p + "resnets.1.", out_pad=2 if (i < 3 and temporal) else 0)
             if i < 3:
-                h = self._conv(h, p + "downsamplers.0.conv", stride_t=2 if temporal else 1, stride_hw=2)
+                h = self._conv(h, p + "downsamplers.0.conv", stride_t=2 if temporal else 1, stride_hw=2, stats=True)
         h = self._mid(h, "encoder.mid_block.")
         h = self._gn(h, "encoder.conv_norm_out", True, 2)
         h = self._conv(h, "encoder.conv_out")

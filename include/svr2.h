@@ -64,6 +64,14 @@ int svr2_conv3d_bf16(const void* x, int T_in_total, int H, int W, int Cin, const
                      int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags, const void* bias,
                      const void* residual, void* y, int out_t_pad, int out_dup_head, int ldc, void* stream);
 
+/* Same conv, additionally emitting per-tile GroupNorm partial sums (fp32, deterministic order) of the stored
+ * output so that the following causal_norm_wrapper needs no statistics pass.  stat_partial: [T_out][slots][Cout/8]
+ * float4; pass NULL to query *stat_slots (bytes needed = T_out * slots * Cout/8 * 16). */
+int svr2_conv3d_stats_bf16(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout, int kt, int kh,
+                           int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags, const void* bias,
+                           const void* residual, void* y, int out_t_pad, int out_dup_head, int ldc, void* stat_partial,
+                           int64_t stat_bytes, int* stat_slots, void* stream);
+
 /* ---- Upsample3D: 1x1x1 conv + 'b (x y z c) f h w -> b c (f z) (h x) (w y)' + remove_head
  * (attn_video_vae.py:135-153, causal_inflation_lib.py:412-419) in one GEMM. */
 int svr2_upsample_shuffle_bf16(const void* x, int F, int H, int W, int C, const void* w, const void* bias,
@@ -108,6 +116,10 @@ int svr2_groupnorm_bf16(const void* x, void* y, int frames, int hw, int C, const
                         float eps, int silu, int out_t_pad, int out_dup_head, double* scratch,
                         int64_t scratch_bytes, void* stream);
 int64_t svr2_groupnorm_scratch_bytes(int frames, int hw, int C);
+/* GroupNorm(+SiLU) from the partial sums of svr2_conv3d_stats_bf16 (finalize + apply; coef_scratch: frames*C*8 B) */
+int svr2_groupnorm_from_stats_bf16(const void* x, void* y, int frames, int hw, int C, const void* gamma,
+                                   const void* beta, float eps, int silu, int out_t_pad, int out_dup_head,
+                                   const void* stat_partial, int stat_slots, void* coef_scratch, void* stream);
 
 /* VAE mid-block attention (1 head, d = 512; attn_video_vae.py:656-668) as two GEMM passes that never
  * materialise the fp32 score matrix: pass 1 = svr2_linear_bf16(..., SVR2_EPI_ROWSTAT) + svr2_rowstat_combine,

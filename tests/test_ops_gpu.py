@@ -313,3 +313,32 @@ def test_two_pass_attention_probabilities(svr2lib, M, n):
     assert_close(lse, torch.logsumexp(S, -1) * 1.4426950408889634, 1e-4, "lse2")
     assert_close(P[:, :n], torch.softmax(S, -1), 6e-3, "probabilities")
     assert (P[:, :n].float().sum(-1) - 1).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("Cin,Cout,T,H,W", [(64, 128, 2, 20, 36), (128, 256, 2, 19, 30), (256, 512, 1, 12, 20)])
+def test_conv_epilogue_groupnorm_stats(svr2lib, Cin, Cout, T, H, W):
+    """svr2_conv3d_stats_bf16 + svr2_groupnorm_from_stats_bf16 == conv followed by per-frame GroupNorm + SiLU."""
+    import ctypes
+    x = rnd(1, Cin, T, H, W, seed=1)
+    w = rnd(Cout, Cin, 3, 3, 3, std=(Cin * 27) ** -0.5, seed=2)
+    b = rnd(Cout, seed=3)
+    x_nd = _to_ndhwc(x, 2)
+    w_k = bf(w.permute(0, 2, 3, 4, 1).reshape(Cout, -1)).contiguous()
+    y = torch.zeros(T, H, W, Cout, device=DEV, dtype=torch.bfloat16)
+    args = (svr2lib.ptr(x_nd), T + 2, H, W, Cin, svr2lib.ptr(w_k), Cout, 3, 3, 3, 1, 1, 1, T, svr2lib.EPI_BIAS,
+            svr2lib.ptr(bf(b)), None, svr2lib.ptr(y), 0, 0, Cout)
+    slots = ctypes.c_int(0)
+    assert svr2lib.load().svr2_conv3d_stats_bf16(*args, None, 0, ctypes.byref(slots), svr2lib.stream()) == 0
+    part = torch.full((T * slots.value * (Cout // 8) * 4,), float("nan"), device=DEV)
+    svr2lib.call("svr2_conv3d_stats_bf16", *args, svr2lib.ptr(part), part.numel() * 4, ctypes.byref(slots),
+                 svr2lib.stream())
+    assert torch.isfinite(part).all(), "every partial slot must be written"
+    gamma, beta = bf(rnd(Cout, seed=4) * 0.1 + 1), bf(rnd(Cout, seed=5) * 0.1)
+    z = torch.zeros(2 + T, H * W, Cout, device=DEV, dtype=torch.bfloat16)
+    coef = torch.empty(T * Cout * 2, device=DEV)
+    svr2lib.call("svr2_groupnorm_from_stats_bf16", svr2lib.ptr(y), svr2lib.ptr(z), T, H * W, Cout, svr2lib.ptr(gamma),
+                 svr2lib.ptr(beta), 1e-6, 1, 2, 1, svr2lib.ptr(part), slots.value, svr2lib.ptr(coef), svr2lib.stream())
+    ref = F.group_norm(y.float().view(T, H * W, Cout).permute(0, 2, 1), 32, gamma.float(), beta.float(), 1e-6)
+    ref = F.silu(bf(ref).float()).permute(0, 2, 1)
+    assert_close(z[2:], ref, 3e-3, "fused-stats groupnorm")
+    assert torch.equal(z[0], z[2]) and torch.equal(z[1], z[2])
