@@ -557,6 +557,43 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const __nv_bfloat16* __res
   }
 }
 
+// ------------------------------------------------------------------ conv_out tap gather
+// Decoder conv_out (128 -> 3, 3x3x3 causal) as (1) one GEMM z[tap*co_n + co][pixel] = W_tap[co,:] . x[pixel,:]
+// over ALL input pixels incl. the 2 halo frames (x is read once instead of 27 times), fp32, and (2) this
+// gather: out[co][t][h][w] = bias[co] + sum_taps z[tap, co][(t+kt), h+kh-1, w+kw-1] (zero outside the frame).
+template <typename TOut>
+__global__ void __launch_bounds__(256) conv_tap_gather_kernel(const float* __restrict__ z, long long ldz, int co_n,
+                                                              const __nv_bfloat16* __restrict__ bias, int T, int H, int W,
+                                                              TOut* __restrict__ out) {
+  const long long hw = (long long)H * W, total = (long long)T * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = i % W, h = (i / W) % H;
+    const long long t = i / hw;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hh = h + kh - 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ww = w + kw - 1;
+          if (ww < 0 || ww >= W) continue;
+          const long long q = (t + kt) * hw + (long long)hh * W + ww;     // halo: input frame index = t + kt
+          const int tap = (kt * 3 + kh) * 3 + kw;
+          for (int c = 0; c < co_n; ++c) acc[c] += z[(long long)(tap * co_n + c) * ldz + q];
+        }
+      }
+    for (int c = 0; c < co_n; ++c) {
+      const float v = bf16_round(acc[c] + __bfloat162float(bias[c]));
+      if constexpr (sizeof(TOut) == 4) out[(long long)c * total + i] = v;
+      else out[(long long)c * total + i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 }  // namespace svr2
 
 using namespace svr2;
@@ -725,4 +762,20 @@ extern "C" int svr2_im2col3_bf16(const void* x, int T, int H, int W, int C, int 
   if (blocks > 148LL * 64) blocks = 148LL * 64;
   im2col3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, T, H, W, C, ld_in, (__nv_bfloat16*)out, ld_out);
   return check_launch("im2col3");
+}
+
+// z: [27*co_n rows][ldz] fp32 (row = tap*co_n + co, column = input pixel incl. 2 halo frames); out: [co_n,T,H,W]
+extern "C" int svr2_conv_tap_gather(const float* z, int64_t ldz, int co_n, const void* bias, int T, int H, int W,
+                                    void* out, int out_dtype, void* stream) {
+  if (co_n < 1 || co_n > 4) return set_error(SVR2_ERR_ARG, "conv_tap_gather: 1 <= co_n <= 4");
+  const long long total = (long long)T * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (out_dtype == 0)
+    conv_tap_gather_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(z, ldz, co_n, (const __nv_bfloat16*)bias, T, H, W, (float*)out);
+  else if (out_dtype == 1)
+    conv_tap_gather_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(z, ldz, co_n, (const __nv_bfloat16*)bias, T, H, W, (__nv_bfloat16*)out);
+  else return set_error(SVR2_ERR_ARG, "conv_tap_gather: dtype must be 0 (f32) or 1 (bf16)");
+  return check_launch("conv_tap_gather");
 }

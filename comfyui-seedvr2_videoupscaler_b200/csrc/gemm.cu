@@ -796,7 +796,7 @@ extern "C" void svr2_set_cta_pair(int on) { g_pair_mode = on ? 1 : 0; }
 // pair tiles are used for the 256/128-column bf16 / SwiGLU kernels when there are at least two m-tiles
 static bool want_pair(int block_n, int epi, int num_m_tiles) {
   if (!pair_mode() || num_m_tiles < 2) return false;
-  if (epi & (EPI_F32 | EPI_ROWSTAT | EPI_PEXP)) return false;
+  (void)epi;
   return block_n == 256;   // 128-column pair tiles lose to swap-AB (855-1042 vs ~1400 TFLOP/s measured)
 }
 
@@ -804,6 +804,9 @@ static int dispatch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& 
                          cudaStream_t s, bool pair = false) {
   if (pair) {
     if (p.epi & EPI_SWIGLU) return launch_gemm<256, KIND_SWIGLU, false, true>(ta, tb, p, s);
+    if (p.epi & EPI_ROWSTAT) return launch_gemm<256, KIND_ROWSTAT, false, true>(ta, tb, p, s);
+    if (p.epi & EPI_PEXP) return launch_gemm<256, KIND_PEXP, false, true>(ta, tb, p, s);
+    if (p.epi & EPI_F32) return launch_gemm<256, KIND_F32, false, true>(ta, tb, p, s);
     return launch_gemm<256, KIND_BF16, false, true>(ta, tb, p, s);
   }
   if (p.epi & EPI_SWIGLU) {

@@ -100,9 +100,9 @@ class B200VideoVAE:
             elif k == "decoder.conv_in.weight":
                 W[k] = self._conv_w(v, cin_pad=64)
             elif k == "decoder.conv_out.weight":
-                W[k] = self._conv_w(v, cout_pad=8)
-            elif k == "decoder.conv_out.bias":
-                W[k] = self._vec(v, 8)
+                # tap-major GEMM operand: row = tap*3 + co, K = 128 input channels (see decode())
+                O, I = v.shape[:2]
+                W[k] = v.to(self.device, torch.bfloat16).permute(2, 3, 4, 0, 1).reshape(27 * O, I).contiguous()
             elif k.endswith(".weight") and v.ndim == 5:
                 W[k] = self._conv_w(v)
             elif k.endswith(".weight") and v.ndim == 4:   # 2-D checkpoint: "tail" inflation (causal_inflation_lib.py:440-457)
@@ -273,9 +273,17 @@ class B200VideoVAE:
             if i < 3:
                 x = self._upsample(x, f"decoder.up_blocks.{i}.upsamplers.0.", temporal=i < 2)
         x = self._gn(x, "decoder.conv_norm_out", True, 2)
-        x = self._conv(x, "decoder.conv_out")
+        # conv_out (128 -> 3): per-tap channel contraction as ONE GEMM over all input pixels (x read once, not
+        # 27 times), fp32 z[tap*3+co][pixel], then the 27-tap spatial/temporal gather writes NCDHW directly.
+        wt = self.W["decoder.conv_out.weight"]                      # [81, 128]
+        npix = (x.pad + x.T) * x.H * x.W
+        ldz = (npix + 3) // 4 * 4
+        z = torch.empty(wt.shape[0], ldz, device=dev, dtype=torch.float32)
+        lib.linear(wt, x.buf.view(npix, x.C), epi=lib.EPI_F32, out=z[:, :npix] if ldz != npix else z)
         out = torch.empty(1, 3, x.T, x.H, x.W, device=dev, dtype=torch.bfloat16)
-        lib.call("svr2_ndhwc_to_ncdhw", lib.ptr(x.buf), 8, 3, x.T, x.H, x.W, lib.ptr(out), 1, lib.stream())
+        lib.call("svr2_conv_tap_gather", lib.ptr(z), ldz, 3, lib.ptr(self.W["decoder.conv_out.bias"]), x.T, x.H, x.W,
+                 lib.ptr(out), 1, lib.stream(), nbytes=4.0 * 81 * npix)
+        del z
         if squeeze:
             out = out.squeeze(2)
         return VAEOutput(sample=out)

@@ -135,6 +135,11 @@ int svr2_ncdhw_to_ndhwc_bf16(const void* in, int in_dtype, int C, int T, int H, 
                              int out_t_pad, float div, void* stream);
 int svr2_ndhwc_to_ncdhw(const void* in, int ld_in, int C, int T, int H, int W, void* out, int out_dtype,
                         void* stream);
+/* Decoder conv_out (128 -> 3; attn_video_vae.py:1031-1033) second half: z[tap*co_n+co][pixel] (fp32, from one
+ * svr2_linear_bf16(weights-as-A, activations-as-B, SVR2_EPI_F32) over all input pixels incl. the halo frames)
+ * -> out[co][t][h][w] = bf16(bias + sum over the 27 taps), NCDHW. */
+int svr2_conv_tap_gather(const float* z, int64_t ldz, int co_n, const void* bias, int T, int H, int W, void* out,
+                         int out_dtype, void* stream);
 /* 3x3x3 im2col for the 3-channel encoder conv_in: x [2+T,H,W,Cpad] -> out [T*H*W, ld_out] (81 real cols) */
 int svr2_im2col3_bf16(const void* x, int T, int H, int W, int C, int ld_in, void* out, int ld_out, void* stream);
 
