@@ -266,6 +266,17 @@ def main():
     g_calls = sum(d["calls"] for n, d in prof.items() if is_gemm(n))
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
     fm = flop_model(frames_pad, H, W)
+    # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of one representative
+    # launch (profiles/ncu_full_r1.json, conv 256->256 3x3x3 at 2x1080x1920 on the CTA-pair kernel)
+    traffic = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_full_r1.json")))["conv256_pair"]
+        traffic = {"bytes_per_launch": (float(cap["dram__bytes_read.sum"]) + float(cap["dram__bytes_write.sum"])) * 1e9,
+                   "algorithmic_bytes_per_launch": (4 + 2) * 1080 * 1920 * 256 * 2.0,
+                   "launch": "conv3d 256->256 3x3x3, 2 frames 1080x1920 (+2 halo frames), ncu --set full",
+                   "tensor_pipe_active_pct": float(cap["sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"])}
+    except Exception:
+        pass
     if args.phases:
         tot = sum(d["ms"] for d in prof.values())
         for n, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
@@ -291,7 +302,7 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (Linear + implicit-GEMM Conv3d + upsample)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": None, "launches": g_calls, "kernel_ms_per_step": g_ms / args.steps,
+                     "traffic": traffic, "launches": g_calls, "kernel_ms_per_step": g_ms / args.steps,
                      "share_of_step": g_ms / ms, "peak_source": peak_src},
         "clocks": sampler.result(),
     }

@@ -1,0 +1,33 @@
+"""One representative launch of each dominant kernel for ncu captures (round-1 profiles)."""
+import os, sys, importlib, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from svr2_import import load_package
+load_package()
+lib = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.lib")
+dev = "cuda"
+which = sys.argv[1]
+def rnd(*s): return torch.randn(*s, device=dev, dtype=torch.bfloat16)
+if which == "conv256":      # pair kernel (cta_group::2), 256 -> 256 at 2 x 1080 x 1920
+    T, H, W, C = 2, 1080, 1920, 256
+    x = rnd(T + 2, H, W, C); w = rnd(C, 27 * C) * 0.01; b = rnd(C); y = torch.empty(T, H, W, C, device=dev, dtype=torch.bfloat16)
+    fn = lambda: lib.conv3d(x, T + 2, H, W, C, w, C, (3, 3, 3), 1, 1, 1, T, y, bias=b)
+elif which == "conv128":    # swap-AB kernel, 128 -> 128 at 2 x 2160 x 3840
+    T, H, W, C = 2, 2160, 3840, 128
+    x = rnd(T + 2, H, W, C); w = rnd(C, 27 * C) * 0.01; b = rnd(C); y = torch.empty(T, H, W, C, device=dev, dtype=torch.bfloat16)
+    fn = lambda: lib.conv3d(x, T + 2, H, W, C, w, C, (3, 3, 3), 1, 1, 1, T, y, bias=b)
+elif which == "swiglu":     # DiT SwiGLU input projection at the 4K shard (L = 97200)
+    L = 97200
+    a = rnd(L, 2560); w = rnd(13824, 2560) * 0.02
+    fn = lambda: lib.linear(a, w, epi=lib.EPI_SWIGLU)
+elif which == "attn":       # DiT window attention at the 4K shard: 243 windows of 405 + 58 tokens, 20 heads
+    lens = [463] * 243; total = sum(lens)
+    q, k, v = rnd(total, 20, 128), rnd(total, 20, 128), rnd(total, 20, 128)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+    o = torch.empty_like(q)
+    fn = lambda: lib.attn_varlen(q, k, v, cu, 463, out=o)
+for _ in range(3): fn()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+print(which, f"{e0.elapsed_time(e1):.3f} ms")
