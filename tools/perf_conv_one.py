@@ -1,6 +1,6 @@
 """One representative launch of each dominant kernel for ncu captures (round-1 profiles)."""
 import os, sys, importlib, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tools/)
 sys.path.insert(0, ROOT)
 from svr2_import import load_package
 load_package()

@@ -2,7 +2,7 @@
 (used for ncu captures and kernel tuning; not a pytest)."""
 import os, sys, time, importlib
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tools/)
 sys.path.insert(0, ROOT)
 from svr2_import import load_package
 load_package()

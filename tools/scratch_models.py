@@ -1,7 +1,7 @@
 """scratch: run on GPU, print PSNRs of the engine vs goldens / oracle."""
 import os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tools/)
 sys.path.insert(0, ROOT)
 from svr2_import import load_package
 pkg = load_package()
