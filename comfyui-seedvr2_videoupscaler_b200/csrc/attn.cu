@@ -31,20 +31,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 constexpr int ATT_BM = 128;      // q rows per CTA
-constexpr int ATT_BN = 128;      // kv rows per tile
+constexpr int ATT_BN = 64;       // kv rows per tile (two CTAs are co-resident per SM: ~82 KB smem each)
 constexpr int ATT_D = 128;
 constexpr int ATT_THREADS = 192;
-constexpr int ATT_KV_STAGES = 2;
-constexpr int ATT_TILE_BYTES = 128 * 128 * 2;       // 32 KB: two [128 x 64] swizzled halves
-constexpr int ATT_HALF_BYTES = ATT_TILE_BYTES / 2;
+constexpr int ATT_Q_BYTES = 128 * 128 * 2;          // 32 KB: two [128 x 64] swizzled halves
+constexpr int ATT_QH_BYTES = ATT_Q_BYTES / 2;
+constexpr int ATT_KV_BYTES = ATT_BN * 128 * 2;      // 16 KB: two [64 x 64] swizzled halves
+constexpr int ATT_KVH_BYTES = ATT_KV_BYTES / 2;
+constexpr int ATT_P_BYTES = 128 * ATT_BN * 2;       // 16 KB: one [128 x 64] swizzled block
 
 struct AttnSmem {
   // offsets inside the 1024-aligned dynamic smem
   static constexpr int kQ = 0;
-  static constexpr int kP = kQ + ATT_TILE_BYTES;
-  static constexpr int kKV = kP + ATT_TILE_BYTES;                       // stage s: K at +0, V at +32K
-  static constexpr int kBar = kKV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES;
-  static constexpr int kTotal = kBar + 256 + 1024;
+  static constexpr int kP = kQ + ATT_Q_BYTES;
+  static constexpr int kK = kP + ATT_P_BYTES;
+  static constexpr int kV = kK + ATT_KV_BYTES;
+  static constexpr int kBar = kV + ATT_KV_BYTES;
+  static constexpr int kTotal = kBar + 128 + 1024;
 };
 
 struct AttnParams {
@@ -55,7 +58,10 @@ struct AttnParams {
   float scale_log2;  // softmax_scale * log2(e)
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+// K and V are single-buffered with separate full/empty barriers: K_{j+1} streams in while tile j is in
+// softmax / P·V, V_{j+1} while tile j+1 is in Q·K^T / softmax; the second CTA on the SM fills the tensor
+// pipe while this one is in its softmax phase.
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   const int seq = blockIdx.y, head = blockIdx.z, qt = blockIdx.x;
@@ -68,8 +74,10 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::kBar);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;                  // [2]
-  uint64_t* kv_empty = bars + 3;                 // [2]
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 2;
+  uint64_t* v_full = bars + 3;
+  uint64_t* v_empty = bars + 4;
   uint64_t* s_full = bars + 5;
   uint64_t* s_free = bars + 6;
   uint64_t* p_ready = bars + 7;
@@ -82,17 +90,17 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
-    for (int i = 0; i < ATT_KV_STAGES; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
     mbar_init(s_free, 128);
     mbar_init(p_ready, 128);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<256>(tmem_slot);     // S: 64 columns, O: 128 columns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -104,57 +112,53 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      mbar_expect_tx(q_full, ATT_Q_BYTES);
       tma_load_2d(smem + AttnSmem::kQ, &tmap_q, q_full, col0, q_row0);
-      tma_load_2d(smem + AttnSmem::kQ + ATT_HALF_BYTES, &tmap_q, q_full, col0 + 64, q_row0);
-      int stage = 0;
-      uint32_t phase = 0;
+      tma_load_2d(smem + AttnSmem::kQ + ATT_QH_BYTES, &tmap_q, q_full, col0 + 64, q_row0);
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* sk = smem + AttnSmem::kKV + stage * 2 * ATT_TILE_BYTES;
-        uint8_t* sv = sk + ATT_TILE_BYTES;
         const int r0 = s_begin + j * ATT_BN;
-        mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
-        tma_load_2d(sk, &tmap_k, &kv_full[stage], col0, r0);
-        tma_load_2d(sk + ATT_HALF_BYTES, &tmap_k, &kv_full[stage], col0 + 64, r0);
-        tma_load_2d(sv, &tmap_v, &kv_full[stage], col0, r0);
-        tma_load_2d(sv + ATT_HALF_BYTES, &tmap_v, &kv_full[stage], col0 + 64, r0);
-        if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1; }
+        mbar_wait(k_empty, (j & 1) ^ 1);
+        mbar_expect_tx(k_full, ATT_KV_BYTES);
+        tma_load_2d(smem + AttnSmem::kK, &tmap_k, k_full, col0, r0);
+        tma_load_2d(smem + AttnSmem::kK + ATT_KVH_BYTES, &tmap_k, k_full, col0 + 64, r0);
+        mbar_wait(v_empty, (j & 1) ^ 1);
+        mbar_expect_tx(v_full, ATT_KV_BYTES);
+        tma_load_2d(smem + AttnSmem::kV, &tmap_v, v_full, col0, r0);
+        tma_load_2d(smem + AttnSmem::kV + ATT_KVH_BYTES, &tmap_v, v_full, col0 + 64, r0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, ATT_BN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // B (=V) is MN-major
       const uint32_t q_addr = smem_u32(smem + AttnSmem::kQ);
       const uint32_t p_addr = smem_u32(smem + AttnSmem::kP);
+      const uint32_t k_addr = smem_u32(smem + AttnSmem::kK);
+      const uint32_t v_addr = smem_u32(smem + AttnSmem::kV);
       mbar_wait(q_full, 0);
-      int stage = 0;
-      uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
-        const uint32_t k_addr = smem_u32(smem + AttnSmem::kKV + stage * 2 * ATT_TILE_BYTES);
-        const uint32_t v_addr = k_addr + ATT_TILE_BYTES;
-        mbar_wait(&kv_full[stage], phase);
+        mbar_wait(k_full, j & 1);
         if (j > 0) mbar_wait(s_free, (j - 1) & 1);     // softmax has finished reading S_{j-1}
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {                 // contraction over d = 128
-          const uint64_t da = umma_desc_kmajor_sw128(q_addr + (kk >> 2) * ATT_HALF_BYTES) + uint64_t((kk & 3) * 2);
-          const uint64_t db = umma_desc_kmajor_sw128(k_addr + (kk >> 2) * ATT_HALF_BYTES) + uint64_t((kk & 3) * 2);
+          const uint64_t da = umma_desc_kmajor_sw128(q_addr + (kk >> 2) * ATT_QH_BYTES) + uint64_t((kk & 3) * 2);
+          const uint64_t db = umma_desc_kmajor_sw128(k_addr + (kk >> 2) * ATT_KVH_BYTES) + uint64_t((kk & 3) * 2);
           umma_bf16(tmem_s, da, db, idesc_qk, kk != 0);
         }
+        umma_commit(k_empty);                            // K_{j+1} may stream in
         umma_commit(s_full);
+        mbar_wait(v_full, j & 1);
         mbar_wait(p_ready, j & 1);                       // P_j in smem, O rescaled
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {                 // contraction over kv = 128 (16 rows per MMA)
-          const uint64_t da = umma_desc_kmajor_sw128(p_addr + (kk >> 2) * ATT_HALF_BYTES) + uint64_t((kk & 3) * 2);
-          const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, ATT_HALF_BYTES, 1024);
+        for (int kk = 0; kk < ATT_BN / 16; ++kk) {       // contraction over the 64 kv rows (16 per MMA)
+          const uint64_t da = umma_desc_kmajor_sw128(p_addr) + uint64_t(kk * 2);
+          const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, ATT_KVH_BYTES, 1024);
           umma_bf16(tmem_o, da, db, idesc_pv, (j | kk) != 0);
         }
-        umma_commit(&kv_empty[stage]);
+        umma_commit(v_empty);
         umma_commit(pv_done);
-        if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -167,18 +171,16 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      uint32_t sv[128];
+      uint32_t sv[ATT_BN];
       tmem_ld32(tmem_s + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
       tmem_ld32(tmem_s + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-      tmem_ld32(tmem_s + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&sv[64]));
-      tmem_ld32(tmem_s + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&sv[96]));
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(s_free);                      // S may be overwritten by the next QK^T
       const int kv_valid = len - j * ATT_BN;    // columns >= kv_valid are padding / next sequence
       float mx = m_run;
 #pragma unroll
-      for (int c = 0; c < 128; ++c) {
+      for (int c = 0; c < ATT_BN; ++c) {
         float s = __uint_as_float(sv[c]);
         s = (c < kv_valid) ? s : -INFINITY;
         sv[c] = __float_as_uint(s);
@@ -187,7 +189,15 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const float alpha = fast_exp2((m_run - mx) * p.scale_log2);   // 0 on the first tile (m_run = -inf)
       const float mb = mx * p.scale_log2;
       float lsum = 0.f;
-      // wait until P_{j-1}·V_{j-1} has completed before touching O or the P buffer
+      // P values first (independent of the previous P·V), then wait for it before touching O / the P buffer
+      uint32_t pk[ATT_BN / 2];
+#pragma unroll
+      for (int c = 0; c < ATT_BN; c += 2) {
+        const float p0 = fast_exp2(__uint_as_float(sv[c]) * p.scale_log2 - mb);
+        const float p1 = fast_exp2(__uint_as_float(sv[c + 1]) * p.scale_log2 - mb);
+        lsum += p0 + p1;
+        pk[c / 2] = pack_bf16x2(p0, p1);
+      }
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
@@ -204,19 +214,11 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           tmem_st_wait();
         }
       }
-      // P = exp2(s*scale - m*scale) -> bf16 -> swizzled K-major smem (row = this thread)
+      // P -> swizzled K-major smem (row = this thread, 8 chunks of 16 B)
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {          // 16-byte chunks of 8 kv columns
-        float pf[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          pf[e] = fast_exp2(__uint_as_float(sv[ch * 8 + e]) * p.scale_log2 - mb);
-          lsum += pf[e];
-        }
-        const int half = ch >> 3, cw = ch & 7;
-        uint8_t* dst = sp + half * ATT_HALF_BYTES + row * 128 + ((cw ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(pf[0], pf[1]), pack_bf16x2(pf[2], pf[3]),
-                                                    pack_bf16x2(pf[4], pf[5]), pack_bf16x2(pf[6], pf[7]));
+      for (int ch = 0; ch < ATT_BN / 8; ++ch) {
+        uint8_t* dst = sp + row * 128 + ((ch ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
       }
       l_run = l_run * alpha + lsum;
       m_run = mx;
@@ -241,11 +243,11 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       if (valid) {
 #pragma unroll
         for (int e = 0; e < 32; e += 8) {
-          uint4 pk = make_uint4(pack_bf16x2(__uint_as_float(o[e]) * inv_l, __uint_as_float(o[e + 1]) * inv_l),
-                                pack_bf16x2(__uint_as_float(o[e + 2]) * inv_l, __uint_as_float(o[e + 3]) * inv_l),
-                                pack_bf16x2(__uint_as_float(o[e + 4]) * inv_l, __uint_as_float(o[e + 5]) * inv_l),
-                                pack_bf16x2(__uint_as_float(o[e + 6]) * inv_l, __uint_as_float(o[e + 7]) * inv_l));
-          *reinterpret_cast<uint4*>(orow + c0 + e) = pk;
+          uint4 pk4 = make_uint4(pack_bf16x2(__uint_as_float(o[e]) * inv_l, __uint_as_float(o[e + 1]) * inv_l),
+                                 pack_bf16x2(__uint_as_float(o[e + 2]) * inv_l, __uint_as_float(o[e + 3]) * inv_l),
+                                 pack_bf16x2(__uint_as_float(o[e + 4]) * inv_l, __uint_as_float(o[e + 5]) * inv_l),
+                                 pack_bf16x2(__uint_as_float(o[e + 6]) * inv_l, __uint_as_float(o[e + 7]) * inv_l));
+          *reinterpret_cast<uint4*>(orow + c0 + e) = pk4;
         }
       }
     }
@@ -277,12 +279,12 @@ extern "C" int svr2_attn_varlen_bf16(const void* q, const void* k, const void* v
   CUtensorMap tq, tk, tv;
   uint64_t dims[2] = {(uint64_t)heads * ATT_D, (uint64_t)total};
   uint64_t strides[1] = {(uint64_t)heads * ATT_D * 2};
-  uint32_t box[2] = {64, 128};
-  int rc = make_tmap_bf16(&tq, q, 2, dims, strides, box);
+  uint32_t box_q[2] = {64, ATT_BM}, box_kv[2] = {64, ATT_BN};
+  int rc = make_tmap_bf16(&tq, q, 2, dims, strides, box_q);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tk, k, 2, dims, strides, box);
+  rc = make_tmap_bf16(&tk, k, 2, dims, strides, box_kv);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tv, v, 2, dims, strides, box);
+  rc = make_tmap_bf16(&tv, v, 2, dims, strides, box_kv);
   if (rc) return rc;
   AttnParams p;
   p.cu_seqlens = cu_seqlens;

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
   for (; i + 3 * stride < nvec; i += 4 * stride) {
     uint4 r[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) r[u] = reinterpret_cast<const uint4*>(xf)[i + u * stride];
+    for (int u = 0; u < 4; ++u) r[u] = __ldcs(reinterpret_cast<const uint4*>(xf) + i + u * stride);   // streamed once
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       float v[8], o[8];
