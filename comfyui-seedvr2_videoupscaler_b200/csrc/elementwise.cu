@@ -528,8 +528,47 @@ __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ in, int 
 }
 
 // 3x3x3 im2col, zero spatial padding, causal halo = 2 real frames in front of x.
-// x [2+T, H, W, ld_in] (C real channels) -> out [T*H*W, ld_out], column ((kt*3+kh)*3+kw)*C + c.
-// One thread produces one 16-byte chunk (8 consecutive columns) of an output row.
+// x [2+T, H, W, 8] (3 real channels: one aligned 16-byte load per pixel) -> out [T*H*W, 128], column
+// ((kt*3+kh)*3+kw)*3 + c, columns 81..127 zero.  One thread assembles one output row in registers
+// (27 pixel loads, mostly L1 hits shared with the neighbouring rows) and writes its 256 bytes.
+__global__ void __launch_bounds__(128) im2col3_c3_kernel(const uint4* __restrict__ x, int T, int H, int W,
+                                                         uint4* __restrict__ out) {
+  const long long total = (long long)T * H * W;
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= total) return;
+  const int w = row % W, h = (row / W) % H;
+  const long long t = row / ((long long)W * H);
+  uint32_t v[44];                      // 88 bf16 slots: 81 values + zero tail
+#pragma unroll
+  for (int i = 0; i < 44; ++i) v[i] = 0;
+#pragma unroll
+  for (int tap = 0; tap < 27; ++tap) {
+    const int kw = tap % 3, kh = (tap / 3) % 3, kt = tap / 9;
+    const int hh = h + kh - 1, ww = w + kw - 1;
+    uint32_t c01 = 0, c2 = 0;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+      const uint4 px = x[((t + kt) * H + hh) * W + ww];
+      c01 = px.x;
+      c2 = px.y & 0xffffu;
+    }
+    // place 3 halfwords at halfword offset 3*tap
+    const int o = 3 * tap;
+    if ((o & 1) == 0) {               // aligned: [c0 c1] -> word o/2, c2 -> low half of word o/2+1
+      v[o / 2] |= c01;
+      v[o / 2 + 1] |= c2;
+    } else {                          // c0 -> high half of word (o-1)/2, [c1 c2] -> next word
+      v[o / 2] |= c01 << 16;
+      v[o / 2 + 1] |= (c01 >> 16) | (c2 << 16);
+    }
+  }
+  uint4* dst = out + row * 16;
+#pragma unroll
+  for (int j = 0; j < 11; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+#pragma unroll
+  for (int j = 11; j < 16; ++j) dst[j] = make_uint4(0, 0, 0, 0);
+}
+
+// generic fallback: one thread per 16-byte chunk
 __global__ void __launch_bounds__(256) im2col3_kernel(const __nv_bfloat16* __restrict__ x, int T, int H, int W, int C,
                                                       int ld_in, __nv_bfloat16* __restrict__ out, int ld_out) {
   const int cpr = ld_out / 8;
@@ -757,6 +796,11 @@ extern "C" int svr2_ndhwc_to_ncdhw(const void* in, int ld_in, int C, int T, int 
 extern "C" int svr2_im2col3_bf16(const void* x, int T, int H, int W, int C, int ld_in, void* out, int ld_out,
                                  void* stream) {
   if (ld_out % 8) return set_error(SVR2_ERR_ARG, "im2col3: ld_out % 8");
+  if (C == 3 && ld_in == 8 && ld_out == 128) {
+    const long long rows = (long long)T * H * W;
+    im2col3_c3_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const uint4*)x, T, H, W, (uint4*)out);
+    return check_launch("im2col3_c3");
+  }
   const long long total = (long long)T * H * W * (ld_out / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 64) blocks = 148LL * 64;

@@ -39,6 +39,7 @@ constexpr int kNumThreads = 384;   // 4 control warps + 8 epilogue warps
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, num_k_blocks;
+  int group_n;           // n-tiles per L2 raster group (tiles run group by group: for group: for m: for n in group)
   // ---- A addressing (conv) ----
   int a_mode;            // 0 linear (2-D [M,K]); 1 conv stride-1 (4-D C,W,H,T); 2 conv spatial stride-2 (5-D pair view)
   int tiles_w, tiles_h;  // M tiles per output frame
@@ -102,6 +103,20 @@ __device__ __forceinline__ void stat_acc(float4& a, const uint4& d) {
     if (e < 2) { a.x += lo + hi; a.y += lo * lo + hi * hi; }
     else { a.z += lo + hi; a.w += lo * lo + hi * hi; }
   }
+}
+
+// L2-aware tile raster: the n-tiles are processed in groups of `g` columns of tiles; inside a group the order is
+// m-major with n fastest, so a group's slice of B (g * BLOCK_N * K * 2 bytes, chosen <= ~24 MB by the host) stays
+// L2-resident while A streams through once per group.  (Plain n-fastest order re-streams all of B from DRAM for
+// every m-row once B exceeds L2 — 132 MB for the 4K VAE attention keys.)
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int g, int& m, int& n) {
+  const int per_group = g * num_m;
+  const int ng = tile / per_group;
+  const int r = tile - ng * per_group;
+  const int n0 = ng * g;
+  const int gsz = (num_n - n0) < g ? (num_n - n0) : g;
+  m = r / gsz;
+  n = n0 + (r - m * gsz);
 }
 
 enum : int { KIND_BF16 = 0, KIND_SWIGLU = 1, KIND_F32 = 2, KIND_ROWSTAT = 3, KIND_PEXP = 4 };
@@ -209,7 +224,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   // tile schedule: 1-CTA: one 128-row m-tile per tile; pair: m-tiles (2j, 2j+1) per tile, same tile in both CTAs
   const int num_n_tiles = p.num_n_tiles;
-  const int num_tiles = (TWO ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * num_n_tiles;
+  const int num_m_sup = TWO ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+  const int num_tiles = num_m_sup * num_n_tiles;
   const int tile0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
@@ -244,7 +260,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       };
       if (a_mode == 0) {
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-          const int m_sup = tile / num_n_tiles, n_blk = tile - m_sup * num_n_tiles;
+          int m_sup, n_blk;
+          tile_coords(tile, num_m_sup, num_n_tiles, p.group_n, m_sup, n_blk);
           const int m_blk = TWO ? 2 * m_sup + (int)cta_rank : m_sup;
           const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N + (TWO ? (int)cta_rank * (BLOCK_N / 2) : 0);
           for (int kb = 0; kb < nkb; ++kb) {
@@ -266,7 +283,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int bw = p.bw, bh = p.bh, pad_h = p.pad_h, pad_w = p.pad_w, stride_t = p.stride_t;
         const int taps_t = p.taps_t, taps_h = p.taps_h, taps_w = p.taps_w, cin_blocks = p.cin_blocks, cin = p.cin;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-          const int m_sup = tile / num_n_tiles, n_blk = tile - m_sup * num_n_tiles;
+          int m_sup, n_blk;
+          tile_coords(tile, num_m_sup, num_n_tiles, p.group_n, m_sup, n_blk);
           const int m_blk = TWO ? 2 * m_sup + (int)cta_rank : m_sup;
           const int t_o = m_blk / per_frame, r = m_blk - t_o * per_frame;
           const int th = r / tiles_w;
@@ -376,7 +394,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_sup = tile / num_n_tiles, n_blk = tile - m_sup * num_n_tiles;
+      int m_sup, n_blk;
+      tile_coords(tile, num_m_sup, num_n_tiles, p.group_n, m_sup, n_blk);
       const int m_blk = TWO ? 2 * m_sup + (int)cta_rank : m_sup;
       if constexpr (SWAP) {
         // accumulator lanes = output channels (this thread: co), columns = the tile's 256 pixels.
@@ -742,9 +761,18 @@ int num_sms() {
 }
 
 template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, TWO>;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, KIND, SWAP, TWO>;
+  GemmParams p = p_in;
+  {
+    // raster group: keep the group's B slice around 24 MB (L2 = 126 MB, shared with A tiles and the output stream)
+    const long long b_tile_bytes = (long long)(SWAP ? BLOCK_M : BLOCK_N) * p.num_k_blocks * BLOCK_K * 2;
+    long long g = (24LL << 20) / (b_tile_bytes > 0 ? b_tile_bytes : 1);
+    if (g < 1) g = 1;
+    if (g > p.num_n_tiles) g = p.num_n_tiles;
+    p.group_n = (int)g;
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
