@@ -39,6 +39,7 @@ constexpr int kNumThreads = 384;   // 4 control warps + 8 epilogue warps
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, num_k_blocks;
+  int band_h;            // conv m-tile raster: tile rows per band (order: band, frame, row in band, column)
   int group_n;           // n-tiles per L2 raster group (tiles run group by group: for group: for m: for n in group)
   // ---- A addressing (conv) ----
   int a_mode;            // 0 linear (2-D [M,K]); 1 conv stride-1 (4-D C,W,H,T); 2 conv spatial stride-2 (5-D pair view)
@@ -105,6 +106,28 @@ __device__ __forceinline__ void stat_acc(float4& a, const uint4& d) {
   }
 }
 
+// Conv m-tile raster.  A causal 3x3x3 conv reads every input frame for three consecutive output frames; in
+// frame-major tile order those three reads are a whole frame apart (GBs) and all miss L2.  Tiles are therefore
+// ordered band-major: a band of `band_h` tile rows is swept over ALL output frames before the next band, so the
+// three temporal taps (and the vertical 3x3 halo inside the band) hit L2.
+__device__ __forceinline__ void conv_tile(const GemmParams& p, int m_blk, int& t_o, int& th, int& tw) {
+  if (m_blk >= p.num_m_tiles) {   // odd tile count in pair mode: the phantom tile reads out-of-bounds (zero) frames
+    t_o = p.T_out; th = 0; tw = 0;
+    return;
+  }
+  const int full = p.T_out * p.band_h * p.tiles_w;          // m-tiles in a full band
+  const int band = m_blk / full;
+  const int r = m_blk - band * full;
+  const int rows_left = p.tiles_h - band * p.band_h;
+  const int rows = rows_left < p.band_h ? rows_left : p.band_h;
+  const int per = rows * p.tiles_w;                          // tiles of this band in one frame
+  t_o = r / per;
+  const int rr = r - t_o * per;
+  const int trow = rr / p.tiles_w;
+  th = band * p.band_h + trow;
+  tw = rr - trow * p.tiles_w;
+}
+
 // L2-aware tile raster: the n-tiles are processed in groups of `g` columns of tiles; inside a group the order is
 // m-major with n fastest, so a group's slice of B (g * BLOCK_N * K * 2 bytes, chosen <= ~24 MB by the host) stays
 // L2-resident while A streams through once per group.  (Plain n-fastest order re-streams all of B from DRAM for
@@ -155,9 +178,8 @@ __device__ __forceinline__ RowDest row_dest(const GemmParams& p, int m_blk, int 
     d.valid = m < p.M;
     d.off = (long long)m * p.ldc + (long long)n_blk * n_cols;
   } else {
-    const int per_frame = p.tiles_w * p.tiles_h;
-    const int t_o = m_blk / per_frame, r = m_blk - t_o * per_frame;
-    const int th = r / p.tiles_w, tw = r - th * p.tiles_w;
+    int t_o, th, tw;
+    conv_tile(p, m_blk, t_o, th, tw);
     const int rh = row / p.bw;
     const int h = th * p.bh + rh;
     const int w = tw * p.bw + (row - rh * p.bw);
@@ -279,16 +301,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
       } else {
-        const int per_frame = p.tiles_w * p.tiles_h, tiles_w = p.tiles_w;
         const int bw = p.bw, bh = p.bh, pad_h = p.pad_h, pad_w = p.pad_w, stride_t = p.stride_t;
         const int taps_t = p.taps_t, taps_h = p.taps_h, taps_w = p.taps_w, cin_blocks = p.cin_blocks, cin = p.cin;
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
           int m_sup, n_blk;
           tile_coords(tile, num_m_sup, num_n_tiles, p.group_n, m_sup, n_blk);
           const int m_blk = TWO ? 2 * m_sup + (int)cta_rank : m_sup;
-          const int t_o = m_blk / per_frame, r = m_blk - t_o * per_frame;
-          const int th = r / tiles_w;
-          const int h0 = th * bh, w0 = (r - th * tiles_w) * bw;
+          int t_o, th, tw;
+          conv_tile(p, m_blk, t_o, th, tw);
+          const int h0 = th * bh, w0 = tw * bw;
           const int n0 = n_blk * (SWAP ? BLOCK_M : BLOCK_N) + (TWO ? (int)cta_rank * (BLOCK_N / 2) : 0);
           int kcol = 0;
           for (int kt_ = 0; kt_ < taps_t; ++kt_) {
@@ -399,10 +420,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int m_blk = TWO ? 2 * m_sup + (int)cta_rank : m_sup;
       if constexpr (SWAP) {
         // accumulator lanes = output channels (this thread: co), columns = the tile's 256 pixels.
-        const int per_frame = p.tiles_w * p.tiles_h;
-        const int t_o = m_blk / per_frame, r = m_blk - t_o * per_frame;
-        const int th = r / p.tiles_w;
-        const int h0 = th * p.bh, w0 = (r - th * p.tiles_w) * p.bw;
+        int t_o, th, tw;
+        conv_tile(p, m_blk, t_o, th, tw);
+        const int r = th * p.tiles_w + tw;                        // tile index within the frame (statistics slot)
+        const int h0 = th * p.bh, w0 = tw * p.bw;
         const int co = n_blk * BLOCK_M + row;
         const float bsc = ((epi & EPI_BIAS) && co < p.N) ? __bfloat162float(bias[co]) : 0.f;
         const long long fbase = (long long)(t_o + p.out_t_pad) * p.out_frame_stride + n_blk * BLOCK_M + q * 32;
@@ -681,8 +702,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 st.x += __shfl_xor_sync(0xffffffffu, st.x, o); st.y += __shfl_xor_sync(0xffffffffu, st.y, o);
                 st.z += __shfl_xor_sync(0xffffffffu, st.z, o); st.w += __shfl_xor_sync(0xffffffffu, st.w, o);
               }
-              const int per_frame = p.tiles_w * p.tiles_h;
-              const int t_o = m_blk / per_frame, rt = m_blk - t_o * per_frame;
+              int t_o, th, tw;
+              conv_tile(p, m_blk, t_o, th, tw);
+              const int rt = th * p.tiles_w + tw;
               if (lane < CPR && col_ok && m_blk < p.num_m_tiles)
                 p.stat_partial[((long long)t_o * p.stat_slots + rt * 4 + q) * (p.N / 8) + (n_base + col) / 8] = st;
             }
@@ -1018,6 +1040,14 @@ static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, con
   p.pad_h = p.pad_w = pad_hw;
   p.stride_t = stride_t;
   p.H_out = H_out; p.W_out = W_out; p.T_out = T_out;
+  {
+    // band of tile rows whose input (all channels, 3 temporal taps) stays L2-resident: <= ~12 MB per frame
+    const long long row_bytes = (long long)bh * stride_hw * W * Cin * 2;
+    long long bhn = (12LL << 20) / (row_bytes > 0 ? row_bytes : 1);
+    if (bhn < 1) bhn = 1;
+    if (bhn > (H_out + bh - 1) / bh) bhn = (H_out + bh - 1) / bh;
+    p.band_h = (kt > 1) ? (int)bhn : (H_out + bh - 1) / bh;   // no temporal reuse for kt = 1: plain frame-major order
+  }
   p.M = T_out * p.tiles_w * p.tiles_h * BLOCK_M;
   p.N = Cout; p.K = K;
   p.num_m_tiles = T_out * p.tiles_w * p.tiles_h;
