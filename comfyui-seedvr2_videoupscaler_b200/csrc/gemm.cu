@@ -428,7 +428,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const float bsc = ((epi & EPI_BIAS) && co < p.N) ? __bfloat162float(bias[co]) : 0.f;
         const long long fbase = (long long)(t_o + p.out_t_pad) * p.out_frame_stride + n_blk * BLOCK_M + q * 32;
         const bool dup_t = p.out_dup_head && t_o == 0;
-        mbar_wait(&tmem_full[acc], acc_phase);
+        mbar_wait_backoff(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_STRIDE;
         unsigned short* slab16 = reinterpret_cast<unsigned short*>(slab);
@@ -504,7 +504,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (TWO && m_blk >= p.num_m_tiles) { dst.valid = 0; dst.dup = 0; }
       const int n_base = n_blk * (KIND == KIND_SWIGLU ? BLOCK_N / 2 : BLOCK_N);   // first output column
 
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait_backoff(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_STRIDE;
 

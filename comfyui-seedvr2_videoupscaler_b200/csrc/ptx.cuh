@@ -54,6 +54,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// long waits (epilogue warps waiting a whole mainloop for their accumulator): back off between polls so the
+// eight spinning warps do not burn issue slots / power under the 1 kW cap
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+}
 
 // ---------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
