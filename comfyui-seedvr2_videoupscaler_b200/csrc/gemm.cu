@@ -266,7 +266,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       auto acquire = [&](uint8_t*& sa, uint64_t*& fb) -> bool {
         const bool mine = (g++ & 1u) == 0u;
         if (mine) {
-          while (!mbar_try_wait(&empty_bar[stage], phase ^ 1)) __nanosleep(64);   // ring full: sleep, the MMA has stages of slack
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           sa = smem + stage * L::kStageBytes;
           fb = &full_bar[stage];
           if constexpr (TWO) {
