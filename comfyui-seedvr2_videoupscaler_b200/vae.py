@@ -14,7 +14,10 @@ conv carries its temporal halo as two real frames in front of frame 0
 (``pad = 2``); the kernel that produces it writes frame 0 into the halo as well
 (first-frame replication, ``extend_head``, ``causal_inflation_lib.py:423-438``).
 The reference's temporal slicing (``slicing_encode/_decode``, ``:1254-1300``) is
-numerically exact, so the whole clip is processed un-sliced here.
+numerically exact; clips that fit in HBM are processed un-sliced, longer ones
+in temporal chunks whose halo frames are the previous chunk's last two frames
+at the same layer (the reference's ``InflatedCausalConv3d.memory``,
+``causal_inflation_lib.py:306-352``) -- bit-identical to the un-sliced result.
 """
 from __future__ import annotations
 
@@ -63,6 +66,8 @@ class B200VideoVAE:
         self.W: Dict[str, torch.Tensor] = {}
         self._load(state_dict)
         self._stats = None
+        self._chunk = None          # {"first": bool, "state": {layer key: last two frames}} while slicing
+        self.split_size = None      # explicit temporal slice length in sample frames (set_causal_slicing)
 
     # ---- weights ---------------------------------------------------------
     def _conv_w(self, w, cin_pad=None, cout_pad=None):
@@ -119,6 +124,21 @@ class B200VideoVAE:
     def to(self, *a, **k):
         return self
 
+    # ---- temporal slicing state -------------------------------------------
+    @property
+    def _first(self) -> bool:
+        return self._chunk is None or self._chunk["first"]
+
+    def _halo(self, y: Act, key: str) -> None:
+        """Slice boundary: the halo of a tensor that feeds a causal conv is the previous slice's tail at the
+        same layer (InflatedCausalConv3d.memory, causal_inflation_lib.py:306-352); remember this slice's tail."""
+        c = self._chunk
+        if c is None or y.pad == 0:
+            return
+        if not c["first"]:
+            y.buf[: y.pad].copy_(c["state"][key])
+        c["state"][key] = y.buf[-y.pad:].clone()
+
     # ---- primitive wrappers ----------------------------------------------
     def _gn(self, x: Act, prefix: str, silu: bool, pad: int) -> Act:
         y = Act(x.T, x.H, x.W, x.C, pad, self.device)
@@ -127,16 +147,18 @@ class B200VideoVAE:
             coef = torch.empty(x.T * x.C * 2, device=self.device, dtype=torch.float32)
             lib.call("svr2_groupnorm_from_stats_bf16", c_void_p(x.body_ptr()), lib.ptr(y.buf), x.T, x.H * x.W, x.C,
                      lib.ptr(self.W[prefix + ".weight"]), lib.ptr(self.W[prefix + ".bias"]), 1e-6, int(silu), pad,
-                     int(pad > 0), lib.ptr(part), slots, lib.ptr(coef), lib.stream(),
+                     int(pad > 0 and self._first), lib.ptr(part), slots, lib.ptr(coef), lib.stream(),
                      nbytes=4.0 * x.T * x.H * x.W * x.C)
+            self._halo(y, prefix)
             return y
         need = lib.load().svr2_groupnorm_scratch_bytes(x.T, x.H * x.W, x.C)
         if self._stats is None or self._stats.numel() * 8 < need:
             self._stats = torch.empty((need + 7) // 8 + 1024, device=self.device, dtype=torch.float64)
         lib.call("svr2_groupnorm_bf16", c_void_p(x.body_ptr()), lib.ptr(y.buf), x.T, x.H * x.W, x.C,
                  lib.ptr(self.W[prefix + ".weight"]), lib.ptr(self.W[prefix + ".bias"]), 1e-6, int(silu), pad,
-                 int(pad > 0), lib.ptr(self._stats), self._stats.numel() * 8, lib.stream(),
+                 int(pad > 0 and self._first), lib.ptr(self._stats), self._stats.numel() * 8, lib.stream(),
                  nbytes=6.0 * x.T * x.H * x.W * x.C)
+        self._halo(y, prefix)
         return y
 
     def _conv(self, x: Act, prefix: str, *, out_pad=0, residual: Optional[Act] = None, stride_t=1, stride_hw=1,
@@ -146,7 +168,15 @@ class B200VideoVAE:
         Cout = cout if cout is not None else w.shape[0]
         Cin = cin if cin is not None else x.C
         assert x.pad == kt - 1, f"{prefix}: conv with kt={kt} needs a {kt - 1}-frame halo, got {x.pad}"
-        T_out = (x.T - 1) // stride_t + 1
+        x_ptr, T_in_total = lib.ptr(x.buf), x.pad + x.T
+        if stride_t == 2 and not self._first:
+            # a later slice of a temporally strided conv continues the global stride phase: one frame of
+            # memory instead of two (kernel - stride, causal_inflation_lib.py:306-352), T_out = T / 2
+            assert x.T % 2 == 0, "temporal slices after the first must hold a multiple of 4 frames"
+            x_ptr, T_in_total = c_void_p(x.buf.data_ptr() + x.frame_elems * 2), x.pad - 1 + x.T
+            T_out = x.T // 2
+        else:
+            T_out = (x.T - 1) // stride_t + 1
         Ho, Wo = (x.H, x.W) if stride_hw == 1 else (x.H // 2, x.W // 2)
         y = Act(T_out, Ho, Wo, w.shape[0], out_pad, self.device)
         res_ptr = None
@@ -156,9 +186,9 @@ class B200VideoVAE:
             res_ptr = c_void_p(residual.body_ptr() - out_pad * y.frame_elems * 2)
         epi = lib.EPI_BIAS | (lib.EPI_RESIDUAL if residual is not None else 0)
         pad_hw = 1 if (stride_hw == 1 and kh == 3) else 0
-        args = (lib.ptr(x.buf), x.pad + x.T, x.H, x.W, Cin, lib.ptr(w), w.shape[0], kt, kh, kw, stride_t, stride_hw,
+        args = (x_ptr, T_in_total, x.H, x.W, Cin, lib.ptr(w), w.shape[0], kt, kh, kw, stride_t, stride_hw,
                 pad_hw, T_out, epi, lib.ptr(self.W[prefix + ".bias"]), res_ptr, lib.ptr(y.buf), out_pad,
-                int(out_pad > 0), w.shape[0])
+                int(out_pad > 0 and self._first), w.shape[0])
         name, extra = "svr2_conv3d_bf16", ()
         if stats and w.shape[0] in (128, 256, 512):
             import ctypes
@@ -174,6 +204,7 @@ class B200VideoVAE:
                  * self.W[prefix + ".weight.real"][1],
                  tag=(f"|{Cin}>{w.shape[0]}|k{kt}{kh}{kw}|s{stride_t}{stride_hw}|{T_out}x{Ho}x{Wo}"
                       if (lib.PROFILER is not None and lib.PROFILER.detail) else ""))
+        self._halo(y, prefix + ":out")
         return y
 
     def _resnet(self, x: Act, p: str, out_pad=0) -> Act:
@@ -242,12 +273,47 @@ class B200VideoVAE:
     def _upsample(self, x: Act, p: str, temporal: bool) -> Act:
         """Upsample3D.forward (attn_video_vae.py:110-174)."""
         z = 2 if temporal else 1
-        T_out = x.T * z - (1 if temporal else 0)
+        first = self._first                       # remove_head only drops (f=0, z=1) of the clip's first slice
+        T_out = x.T * z - (1 if temporal and first else 0)
         y = Act(T_out, 2 * x.H, 2 * x.W, x.C, 2, self.device)
         lib.call("svr2_upsample_shuffle_bf16", c_void_p(x.body_ptr()), x.T, x.H, x.W, x.C,
-                 lib.ptr(self.W[p + "upscale_conv.weight"]), lib.ptr(self.W[p + "upscale_conv.bias"]), int(temporal), 1,
-                 lib.ptr(y.buf), 2, 1, lib.stream(), flops=2.0 * x.T * x.H * x.W * x.C * 4 * z * x.C)
+                 lib.ptr(self.W[p + "upscale_conv.weight"]), lib.ptr(self.W[p + "upscale_conv.bias"]), int(temporal),
+                 int(first), lib.ptr(y.buf), 2, int(first), lib.stream(),
+                 flops=2.0 * x.T * x.H * x.W * x.C * 4 * z * x.C)
+        self._halo(y, p + "shuffle")
         return self._conv(y, p + "conv", stats=True)
+
+    # ---- temporal slice planning -------------------------------------------
+    BYTES_PER_PIXEL_FRAME = 1500     # measured peak working set of one full-resolution frame (decode or encode)
+
+    def _frames_that_fit(self, H: int, W: int) -> int:
+        free, _ = torch.cuda.mem_get_info(self.device)
+        free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        return max(1, int(0.85 * free) // (self.BYTES_PER_PIXEL_FRAME * H * W))
+
+    @staticmethod
+    def _plan(T: int, size: int):
+        """[start, stop) slices like the reference (slicing_encode/_decode, attn_video_vae.py:1254-1300):
+        the first slice is frame 0 plus ``size`` frames, every later one ``size`` frames."""
+        if T - 1 <= size:
+            return [(0, T)]
+        cuts = [(0, 1 + size)]
+        while cuts[-1][1] < T:
+            cuts.append((cuts[-1][1], min(T, cuts[-1][1] + size)))
+        return cuts
+
+    def _run_sliced(self, fn, src: torch.Tensor, cuts):
+        if len(cuts) == 1:
+            return fn(src)
+        outs = []
+        self._chunk = {"first": True, "state": {}}
+        try:
+            for a, b in cuts:
+                outs.append(fn(src[:, a:b].contiguous()))
+                self._chunk["first"] = False
+        finally:
+            self._chunk = None
+        return torch.cat(outs, dim=2)
 
     # ---- public API --------------------------------------------------------
     @torch.no_grad()
@@ -260,11 +326,24 @@ class B200VideoVAE:
             z = z.unsqueeze(2)
         assert z.shape[0] == 1 and z.shape[1] == 16
         _, _, T, h, w = z.shape
+        zin = z[0].to(self.device)
+        size = max(1, self._frames_that_fit(8 * h, 8 * w) // 4)     # latent frames per slice
+        if self.split_size is not None:
+            size = min(size, max(1, self.split_size // 4))
+        out = self._run_sliced(self._decode_slice, zin, self._plan(T, size))
+        if squeeze:
+            out = out.squeeze(2)
+        return VAEOutput(sample=out)
+
+    def _decode_slice(self, zin: torch.Tensor) -> torch.Tensor:
+        """One temporal slice: zin (16,T,h,w) -> (1,3,T',8h,8w), T' = 4T-3 for the clip's first slice else 4T."""
         dev = self.device
-        zin = z[0].to(dev).contiguous()
+        zin = zin.contiguous()
+        _, T, h, w = zin.shape
         dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[zin.dtype]
         x = Act(T, h, w, 64, 2, dev)
         lib.call("svr2_ncdhw_to_ndhwc_bf16", lib.ptr(zin), dt, 16, T, h, w, lib.ptr(x.buf), 64, 2, 1.0, lib.stream())
+        self._halo(x, "decoder.in")
         x = self._conv(x, "decoder.conv_in", stats=True)
         x = self._mid(x, "decoder.mid_block.")
         for i in range(4):
@@ -283,10 +362,7 @@ class B200VideoVAE:
         out = torch.empty(1, 3, x.T, x.H, x.W, device=dev, dtype=torch.bfloat16)
         lib.call("svr2_conv_tap_gather", lib.ptr(z), ldz, 3, lib.ptr(self.W["decoder.conv_out.bias"]), x.T, x.H, x.W,
                  lib.ptr(out), 1, lib.stream(), nbytes=4.0 * 81 * npix)
-        del z
-        if squeeze:
-            out = out.squeeze(2)
-        return VAEOutput(sample=out)
+        return out
 
     @torch.no_grad()
     def encode(self, x: torch.Tensor, return_dict=True, tiled=False, tile_size=None, tile_overlap=None):
@@ -299,11 +375,26 @@ class B200VideoVAE:
             x = x.unsqueeze(2)
         assert x.shape[0] == 1 and x.shape[1] == 3
         _, _, T, H, Wd = x.shape
+        xin = x[0].to(self.device)
+        size = max(4, self._frames_that_fit(H, Wd) // 4 * 4)        # sample frames per slice, a multiple of 4
+        if self.split_size is not None:
+            size = min(size, max(4, self.split_size // 4 * 4))
+        # slices continue the stride-2 phase of the temporal downsamplers only for clips of 4n+1 frames
+        cuts = self._plan(T, size) if (T - 1) % 4 == 0 else [(0, T)]
+        out = self._run_sliced(self._encode_slice, xin, cuts)
+        if squeeze:
+            out = out.squeeze(2)
+        return VAEOutput(latent=out, latent_dist=None)
+
+    def _encode_slice(self, xin: torch.Tensor) -> torch.Tensor:
+        """One temporal slice: xin (3,T,H,W) -> (1,16,T',H/8,W/8); T = 1+4k for the first slice, 4k after."""
         dev = self.device
-        xin = x[0].to(dev).contiguous()
+        xin = xin.contiguous()
+        _, T, H, Wd = xin.shape
         dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[xin.dtype]
         x8 = torch.empty(2 + T, H, Wd, 8, device=dev, dtype=torch.bfloat16)
         lib.call("svr2_ncdhw_to_ndhwc_bf16", lib.ptr(xin), dt, 3, T, H, Wd, lib.ptr(x8), 8, 2, 1.0, lib.stream())
+        self._halo(Act(T, H, Wd, 8, 2, dev, buf=x8), "encoder.in")
         col = torch.empty(T * H * Wd, 128, device=dev, dtype=torch.bfloat16)
         lib.call("svr2_im2col3_bf16", lib.ptr(x8), T, H, Wd, 3, 8, lib.ptr(col), 128, lib.stream())
         h = Act(T, H, Wd, 128, 0, dev)
@@ -322,9 +413,7 @@ class B200VideoVAE:
         h = self._conv(h, "encoder.conv_out")
         out = torch.empty(1, 16, h.T, h.H, h.W, device=dev, dtype=torch.bfloat16)
         lib.call("svr2_ndhwc_to_ncdhw", lib.ptr(h.buf), 32, 16, h.T, h.H, h.W, lib.ptr(out), 1, lib.stream())
-        if squeeze:
-            out = out.squeeze(2)
-        return VAEOutput(latent=out, latent_dist=None)
+        return out
 
     # reference wrapper surface used by the pipeline (model_configuration.py:1247-1276)
     def preprocess(self, x):
@@ -334,7 +423,9 @@ class B200VideoVAE:
         return x
 
     def set_causal_slicing(self, *, split_size=None, memory_device=None):
-        pass  # slicing is exact in the reference; the engine chooses its own chunking
+        """attn_video_vae.py:1709-1723: ``split_size`` sample frames per temporal slice (latent slices hold
+        split_size // 4).  Slicing is exact; None lets the engine slice only when the clip does not fit in HBM."""
+        self.split_size = split_size
 
     def set_memory_limit(self, conv_max_mem=None, norm_max_mem=None):
         pass

@@ -1,5 +1,6 @@
 """CPU: the C-ABI library loads and exports every symbol include/svr2.h declares (no compute
 calls without a GPU); host-side integer logic (windows, layouts, padding, sharding)."""
+import importlib
 import os
 import re
 
@@ -102,3 +103,15 @@ def test_padding_and_partition(pkg):
     assert shard.partition_frames(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert shard.partition_frames(10, 3, overlap=2) == [(0, 6), (4, 9), (7, 10)]
     assert shard.partition_frames(0, 2) == [(0, 0), (0, 0)]
+
+
+def test_vae_slice_plan_matches_reference_split(pkg):
+    """slicing_encode/_decode (attn_video_vae.py:1254-1300): frame 0 rides with the first slice."""
+    vae = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.vae")
+    plan = vae.B200VideoVAE._plan
+    assert plan(17, 4) == [(0, 5), (5, 9), (9, 13), (13, 17)]
+    assert plan(5, 4) == [(0, 5)] and plan(1, 4) == [(0, 1)]
+    assert plan(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    for T, size in ((33, 8), (21, 4), (6, 1)):
+        cuts = plan(T, size)
+        assert cuts[0][0] == 0 and cuts[-1][1] == T and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
