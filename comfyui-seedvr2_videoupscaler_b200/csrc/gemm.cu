@@ -504,6 +504,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (TWO && m_blk >= p.num_m_tiles) { dst.valid = 0; dst.dup = 0; }
       const int n_base = n_blk * (KIND == KIND_SWIGLU ? BLOCK_N / 2 : BLOCK_N);   // first output column
 
+      // Wide path (64-column phases): per-column operands live in lane registers (lane l holds columns 2l, 2l+1
+      // of the phase) and are broadcast by shuffle in phase 1; they are fetched before the accumulator wait so
+      // the global-load latency never sits on the epilogue's critical path.
+      constexpr bool kWide = (KIND == KIND_BF16 || KIND == KIND_PEXP) && PH_COLS == 64;
+      constexpr int N_PH = kWide ? COLS_W / 64 : 1;
+      uint32_t bias_pk[N_PH];
+      float2 gate2[N_PH];
+      if constexpr (kWide && KIND == KIND_BF16) {
+#pragma unroll
+        for (int ph = 0; ph < N_PH; ++ph) {
+          const int cn = n_base + col_lo + ph * 64 + 2 * lane;
+          const bool ok = cn < p.N;
+          bias_pk[ph] = ((epi & EPI_BIAS) && ok) ? *reinterpret_cast<const uint32_t*>(bias + cn) : 0u;
+          gate2[ph] = ((epi & EPI_GATE) && ok) ? *reinterpret_cast<const float2*>(gate + cn) : make_float2(0.f, 0.f);
+        }
+      }
+
       mbar_wait_backoff(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_STRIDE;
@@ -518,26 +535,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         float mx = -INFINITY, sum = 0.f;
         if (active) {
           const float sc = p.out_scale;
+          constexpr int RS = COLS_W >= 64 ? 64 : 32;      // columns in flight per step
 #pragma unroll 1
-          for (int c0 = col_lo; c0 < col_lo + COLS_W; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(t_addr + c0, v);
+          for (int c0 = col_lo; c0 < col_lo + COLS_W; c0 += RS) {
+            uint32_t v[RS];
+            tmem_ld32(t_addr + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            if constexpr (RS == 64) tmem_ld32(t_addr + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
             tmem_ld_wait();
             const int n0 = n_base + c0;
-            float cm = -INFINITY;
+            if (sc > 0.f && n0 + RS <= p.N) {
+              // interior step: max on the raw accumulators, the scale folded into the exponent's FMA
+              float cm = __uint_as_float(v[0]);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float t = (n0 + j < p.N) ? __uint_as_float(v[j]) * sc : -INFINITY;
-              v[j] = __float_as_uint(t);
-              cm = fmaxf(cm, t);
-            }
-            const float m_new = fmaxf(mx, cm);
-            if (m_new > -INFINITY) {
-              float cs = 0.f;
+              for (int j = 1; j < RS; ++j) cm = fmaxf(cm, __uint_as_float(v[j]));
+              const float m_new = fmaxf(mx, cm * sc);
+              float cs0 = 0.f, cs1 = 0.f;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) cs += exp2_approx(__uint_as_float(v[j]) - m_new);
-              sum = sum * exp2_approx(mx - m_new) + cs;
+              for (int j = 0; j < RS; j += 2) {
+                cs0 += exp2_approx(fmaf(__uint_as_float(v[j]), sc, -m_new));
+                cs1 += exp2_approx(fmaf(__uint_as_float(v[j + 1]), sc, -m_new));
+              }
+              sum = sum * exp2_approx(mx - m_new) + (cs0 + cs1);
               mx = m_new;
+            } else {
+              float cm = -INFINITY;
+#pragma unroll
+              for (int j = 0; j < RS; ++j) {
+                const float t = (n0 + j < p.N) ? __uint_as_float(v[j]) * sc : -INFINITY;
+                v[j] = __float_as_uint(t);
+                cm = fmaxf(cm, t);
+              }
+              const float m_new = fmaxf(mx, cm);
+              if (m_new > -INFINITY) {
+                float cs = 0.f;
+#pragma unroll
+                for (int j = 0; j < RS; ++j) cs += exp2_approx(__uint_as_float(v[j]) - m_new);
+                sum = sum * exp2_approx(mx - m_new) + cs;
+                mx = m_new;
+              }
             }
           }
         }
@@ -555,6 +590,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
         for (int ph0 = col_lo; ph0 < col_lo + COLS_W; ph0 += PH_COLS) {
           // ---------------- phase 1 ----------------
+          if constexpr (kWide) {
+            // both 32-column TMEM chunks of the phase in flight at once; every bf16 rounding point is one
+            // cvt.rn.bf16x2 on a column pair (identical to bf16_rne, half the instructions), and the packed
+            // pair is what gets staged
+            uint32_t v0[32], v1[32];
+            tmem_ld32(t_addr + ph0, v0);
+            tmem_ld32(t_addr + ph0 + 32, v1);
+            tmem_ld_wait();
+            if (ph0 + PH_COLS >= col_lo + COLS_W) {   // all TMEM reads of this warp are done for this tile
+              tc_fence_before();
+              tmem_empty_arrive(&tmem_empty[acc]);
+            }
+            const int phi = (ph0 - col_lo) / 64;
+            uint32_t pk[32];
+            const float sc = p.out_scale;
+            const bool plain = !(epi & (EPI_GELU | EPI_SILU | EPI_GATE));
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float a = __uint_as_float(i < 16 ? v0[2 * (i & 15)] : v1[2 * (i & 15)]);
+              float b = __uint_as_float(i < 16 ? v0[2 * (i & 15) + 1] : v1[2 * (i & 15) + 1]);
+              if constexpr (KIND == KIND_PEXP) {
+                pk[i] = pack_bf16x2(exp2_approx(fmaf(a, sc, -row_lse)), exp2_approx(fmaf(b, sc, -row_lse)));
+              } else {
+                if (epi & EPI_BIAS) {
+                  const uint32_t bw_ = __shfl_sync(0xffffffffu, bias_pk[phi], i);
+                  a += __uint_as_float(bw_ << 16);
+                  b += __uint_as_float(bw_ & 0xffff0000u);
+                }
+                uint32_t r = pack_bf16x2(a, b);
+                if (!plain) {
+                  if (epi & EPI_GELU) {
+                    r = pack_bf16x2(gelu_tanh_fast(__uint_as_float(r << 16)), gelu_tanh_fast(__uint_as_float(r & 0xffff0000u)));
+                  }
+                  if (epi & EPI_SILU) {
+                    r = pack_bf16x2(silu_fast(__uint_as_float(r << 16)), silu_fast(__uint_as_float(r & 0xffff0000u)));
+                  }
+                  if (epi & EPI_GATE) {
+                    const float g0 = __shfl_sync(0xffffffffu, gate2[phi].x, i);
+                    const float g1 = __shfl_sync(0xffffffffu, gate2[phi].y, i);
+                    r = pack_bf16x2(__uint_as_float(r << 16) * g0, __uint_as_float(r & 0xffff0000u) * g1);
+                  }
+                }
+                pk[i] = r;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<uint4*>(slab + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                  make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          } else {
 #pragma unroll 1
           for (int c0 = ph0; c0 < ph0 + PH_COLS; c0 += 32) {
             uint32_t v[32];
@@ -564,10 +649,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               uint32_t u[32];
               tmem_ld32(t_addr + ACC_STRIDE / 2 + c0, u);
               tmem_ld_wait();
+              // rounding points of the reference's bf16 flow (gate, in, silu(gate), product), one
+              // cvt.rn.bf16x2 per column pair each; v[0..15] end up holding the packed output pairs
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float g0 = bf16_rne(__uint_as_float(v[j])), u0 = bf16_rne(__uint_as_float(u[j]));
-                v[j] = __float_as_uint(bf16_rne(bf16_rne(silu_fast(g0)) * u0));
+              for (int i = 0; i < 16; ++i) {
+                const uint32_t rg = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                const uint32_t ru = pack_bf16x2(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1]));
+                const uint32_t rs = pack_bf16x2(silu_fast(__uint_as_float(rg << 16)),
+                                                silu_fast(__uint_as_float(rg & 0xffff0000u)));
+                v[i] = pack_bf16x2(__uint_as_float(rs << 16) * __uint_as_float(ru << 16),
+                                   __uint_as_float(rs & 0xffff0000u) * __uint_as_float(ru & 0xffff0000u));
               }
             } else if constexpr (KIND == KIND_F32) {
               tmem_ld_wait();
@@ -626,6 +717,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 *reinterpret_cast<uint4*>(slab + lane * 128 + ch * 16) =
                     make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
               }
+            } else if constexpr (KIND == KIND_SWIGLU) {
+              const int cbase = (c0 - ph0) / 8;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int ch = (cbase + j) ^ (lane & (CPR - 1));
+                *reinterpret_cast<uint4*>(slab + lane * 128 + ch * 16) =
+                    make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
             } else {
               // values are already bf16-representable: packing is a byte permute (no conversion)
               const int cbase = (c0 - ph0) / 8;
@@ -642,6 +741,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc_fence_before();
             tmem_empty_arrive(&tmem_empty[acc]);
           }
+          }   // !kWide
           __syncwarp();
           // ---------------- phase 2 ----------------
           const int ch = lane % CPR, rsub = lane / CPR;

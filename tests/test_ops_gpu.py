@@ -159,8 +159,9 @@ def test_upsample_shuffle(svr2lib, C, temporal, F_, H, W):
     T_out = y.shape[2]
     out = torch.zeros(2 + T_out, 2 * H, 2 * W, C, device=DEV, dtype=torch.bfloat16)
     x_nd = _to_ndhwc(x, 0)
-    svr2lib.call("svr2_upsample_shuffle_bf16", svr2lib.ptr(x_nd), F_, H, W, C, svr2lib.ptr(bf(w).contiguous()),
-                 svr2lib.ptr(bf(b)), temporal, 1, svr2lib.ptr(out), 2, 1, svr2lib.stream())
+    w16, b16 = bf(w).contiguous(), bf(b)          # keep the operands alive across the launch
+    svr2lib.call("svr2_upsample_shuffle_bf16", svr2lib.ptr(x_nd), F_, H, W, C, svr2lib.ptr(w16),
+                 svr2lib.ptr(b16), temporal, 1, svr2lib.ptr(out), 2, 1, svr2lib.stream())
     assert_close(out[2:], y[0].permute(1, 2, 3, 0), 4e-3, "upsample shuffle")
     assert torch.equal(out[0], out[2]) and torch.equal(out[1], out[2])
 
@@ -325,8 +326,9 @@ def test_conv_epilogue_groupnorm_stats(svr2lib, Cin, Cout, T, H, W):
     x_nd = _to_ndhwc(x, 2)
     w_k = bf(w.permute(0, 2, 3, 4, 1).reshape(Cout, -1)).contiguous()
     y = torch.zeros(T, H, W, Cout, device=DEV, dtype=torch.bfloat16)
+    b16 = bf(b)                                   # must outlive the launch (a temporary's block gets reused by `part`)
     args = (svr2lib.ptr(x_nd), T + 2, H, W, Cin, svr2lib.ptr(w_k), Cout, 3, 3, 3, 1, 1, 1, T, svr2lib.EPI_BIAS,
-            svr2lib.ptr(bf(b)), None, svr2lib.ptr(y), 0, 0, Cout)
+            svr2lib.ptr(b16), None, svr2lib.ptr(y), 0, 0, Cout)
     slots = ctypes.c_int(0)
     assert svr2lib.load().svr2_conv3d_stats_bf16(*args, None, 0, ctypes.byref(slots), svr2lib.stream()) == 0
     part = torch.full((T * slots.value * (Cout // 8) * 4,), float("nan"), device=DEV)

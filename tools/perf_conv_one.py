@@ -26,6 +26,17 @@ elif which == "attn":       # DiT window attention at the 4K shard: 243 windows 
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
     o = torch.empty_like(q)
     fn = lambda: lib.attn_varlen(q, k, v, cu, 463, out=o)
+elif which == "upsample":   # Upsample3D 1x1x1 conv + pixel shuffle, 256 ch at 2 x 1080 x 1920 -> 2 x 2160 x 3840
+    from ctypes import c_void_p
+    T, H, W, C = 2, 1080, 1920, 256
+    x = rnd(T, H, W, C); w = rnd(4 * C, C) * 0.05; b = rnd(4 * C)
+    y = torch.empty(T + 2, 2 * H, 2 * W, C, device=dev, dtype=torch.bfloat16)
+    fn = lambda: lib.call("svr2_upsample_shuffle_bf16", lib.ptr(x), T, H, W, C, lib.ptr(w), lib.ptr(b), 0, 1,
+                          lib.ptr(y), 2, 1, lib.stream())
+elif which == "shortcut":   # 1x1x1 conv_shortcut 256 -> 128 at 2 x 2160 x 3840 (swap-AB, 4 k-blocks per tile)
+    T, H, W, C = 2, 2160, 3840, 256
+    x = rnd(T, H, W, C); w = rnd(128, C) * 0.05; b = rnd(128); y = torch.empty(T, H, W, 128, device=dev, dtype=torch.bfloat16)
+    fn = lambda: lib.conv3d(x, T, H, W, C, w, 128, (1, 1, 1), 1, 1, 0, T, y, bias=b)
 for _ in range(3): fn()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
