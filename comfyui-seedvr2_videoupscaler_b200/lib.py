@@ -48,6 +48,13 @@ SIGNATURES = {
     "svr2_ndhwc_to_ncdhw": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
     "svr2_conv_tap_gather": [_P, c_int64, c_int, _P, c_int, c_int, c_int, _P, c_int, _P],
     "svr2_im2col3_bf16": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
+    "svr2_wavelet_level_bf16": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P],
+    "svr2_adain_bf16": [_P, _P, _P, c_int, c_int64, _P, _P],
+    "svr2_rgb_to_lab_f32": [_P, _P, c_int, c_int64, _P],
+    "svr2_lab_to_rgb_bf16": [_P, _P, _P, _P, c_float, _P, c_int, c_int64, _P],
+    "svr2_histogram_match_scratch_bytes": [c_int64],
+    "svr2_histogram_match_f32": [_P, _P, _P, c_int64, _P, c_int64, _P],
+    "svr2_sample_to_image_bf16": [_P, _P, c_int, c_int64, _P],
 }
 
 _lib = None

@@ -143,6 +143,35 @@ int svr2_conv_tap_gather(const float* z, int64_t ldz, int co_n, const void* bias
 /* 3x3x3 im2col for the 3-channel encoder conv_in: x [2+T,H,W,Cpad] -> out [T*H*W, ld_out] (81 real cols) */
 int svr2_im2col3_bf16(const void* x, int T, int H, int W, int C, int ld_in, void* out, int ld_out, void* stream);
 
+/* ---- Post-decode colour correction + image formatting (phase 4 of the reference pipeline,
+ * generation_phases.py:1236-1345).  Planar bf16 images [planes = T*3][H][W] in [-1,1].
+ *
+ * One level of the wavelet pyramid of wavelet_decomposition (src/utils/color_fix.py:122-184):
+ *   low = bf16(blur_r(img)), 3x3 (1,2,1)x(1,2,1)/16, dilation r = min(radius, max(1, min(H,W)/8)), replicate pad;
+ *   high (optional, in place) = bf16(bf16(high + img) - low)   [first != 0: high starts at zero];
+ *   add_to/out (optional, replaces the `low` store) : out = clamp(bf16(add_to + low), -1, 1) — the recombination
+ *   of wavelet_reconstruction (color_fix.py:187-246) fused into the last level of the style pass. */
+int svr2_wavelet_level_bf16(const void* img, void* low, void* high, const void* add_to, void* out, int planes, int H,
+                            int W, int radius, int first, void* stream);
+/* adaptive_instance_normalization (color_fix.py:72-119): per plane, out = (c - mean_c) / std_c * std_s + mean_s with
+ * unbiased variance, eps 1e-5 and the reference's bf16 rounding points.  stats_scratch: planes * 4 floats. */
+int svr2_adain_bf16(const void* content, const void* style, void* out, int planes, int64_t hw, float* stats_scratch,
+                    void* stream);
+/* _rgb_to_lab_batch (color_fix.py:299-321, 368-413): rgb [frames,3,hw] bf16 in [-1,1] -> lab [3][frames*hw] fp32 */
+int svr2_rgb_to_lab_f32(const void* rgb, float* lab, int frames, int64_t hw, void* stream);
+/* luminance blend + _lab_to_rgb_batch (color_fix.py:333-357, 416-474): L = L_content * w + L_matched * (1 - w)
+ * (L_matched may be NULL: L = L_content), a, b [frames*hw] fp32 -> rgb [frames,3,hw] bf16 in [-1,1] */
+int svr2_lab_to_rgb_bf16(const float* L_content, const float* L_matched, const float* a, const float* b,
+                         float luminance_weight, void* rgb, int frames, int64_t hw, void* stream);
+/* _histogram_matching_channel (color_fix.py:477-521) for equally sized inputs: the r-th smallest source element is
+ * replaced by the r-th smallest reference value (radix sorts + scatter). */
+int64_t svr2_histogram_match_scratch_bytes(int64_t n);
+int svr2_histogram_match_f32(const float* source, const float* reference, float* out, int64_t n, void* scratch,
+                             int64_t scratch_bytes, void* stream);
+/* final formatting (generation_phases.py:1322-1345): sample [frames,3,hw] bf16 -> image [frames,hw,3] bf16,
+ * clamp(-1,1) * 0.5 + 0.5 */
+int svr2_sample_to_image_bf16(const void* sample, void* image, int frames, int64_t hw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import dit_oracle, vae_oracle  # noqa: E402
+from oracle import ref_import  # noqa: E402
 from oracle.ref_import import import_reference_dit, import_reference_vae  # noqa: E402
 from svr2_import import load_package  # noqa: E402
 
@@ -140,12 +141,67 @@ def run_vae_cases():
                             meta=np.array(shp))
 
 
+# ---- post-decode colour correction (src/utils/color_fix.py): name -> (T, H, W)
+COLOR_CASES = {
+    "color_t2_40x56": (2, 40, 56),        # min(H,W)//8 = 5 caps the dilation of levels 3, 4
+    "color_t1_72x96": (1, 72, 96),
+    "color_t3_130x150": (3, 130, 150),    # all five dilations (1..16) un-capped, odd width
+}
+COLOR_METHODS = ("wavelet", "adain", "lab")
+
+
+def color_inputs(T, H, W, seed=7):
+    """(content, style) bf16 [T,3,H,W] in [-1,1]: a smooth scene plus detail (content) / a colour-shifted,
+    softer version of it (style) — what the decoder output and the resized input clip look like."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.nn.functional.interpolate(torch.randn(T, 3, H // 8 + 1, W // 8 + 1, generator=g), size=(H, W),
+                                           mode="bilinear", align_corners=False)
+    content = (base + 0.15 * torch.randn(T, 3, H, W, generator=g)).clamp(-1, 1).to(torch.bfloat16)
+    style = (0.8 * base + 0.1 + 0.05 * torch.randn(T, 3, H, W, generator=g)).clamp(-1, 1).to(torch.bfloat16)
+    return content, style
+
+
+def run_color_cases():
+    """Reference outputs of src/utils/color_fix.py on CPU bf16 inputs; the oracle must reproduce wavelet / AdaIN
+    bit for bit and LAB up to the tie order of the reference's unstable sort."""
+    import importlib
+    if ref_import.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, ref_import.REFERENCE_ROOT)
+    ref = importlib.import_module("src.utils.color_fix")
+    from oracle import color_oracle as co
+
+    class _Dbg:
+        def log(self, *a, **k):
+            pass
+
+    for name, (T, H, W) in COLOR_CASES.items():
+        content, style = color_inputs(T, H, W)
+        outs = {
+            "wavelet": ref.wavelet_reconstruction(content.clone(), style.clone(), _Dbg()),
+            "adain": ref.adaptive_instance_normalization(content.clone(), style.clone()),
+            "lab": ref.lab_color_transfer(content.clone(), style.clone(), _Dbg(), luminance_weight=0.8),
+        }
+        assert all(v.dtype == torch.bfloat16 for v in outs.values())
+        assert torch.equal(outs["wavelet"].float(), co.wavelet_reconstruction(content, style)), name
+        assert torch.equal(outs["adain"].float(), co.adaptive_instance_normalization(content, style)), name
+        lab_o = co.lab_color_transfer(content, style)
+        same = (outs["lab"].float() == lab_o).float().mean().item()
+        mse = ((outs["lab"].float() - lab_o) ** 2).mean().item()
+        psnr = 99.0 if mse == 0 else 10 * np.log10(4.0 / mse)
+        assert same > 0.99 and psnr > 60.0, (name, same, psnr)
+        print(f"{name}: wavelet/adain oracle == reference (bit-exact); lab {100 * same:.2f}% equal, {psnr:.1f} dB")
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"),
+                            **{k: v.float().numpy().astype(np.float32) for k, v in outs.items()})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
-    for name in DIT_CASES:
-        run_dit_case(name)
-    run_vae_cases()
+    if "--color-only" not in sys.argv:
+        for name in DIT_CASES:
+            run_dit_case(name)
+        run_vae_cases()
+    run_color_cases()
 
 
 if __name__ == "__main__":

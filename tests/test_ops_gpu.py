@@ -144,7 +144,9 @@ def test_conv3d(svr2lib, Cin, Cout, k, st, shw, T, H, W):
     assert torch.equal(y[0], y[2]) and torch.equal(y[1], y[2]), "halo frames must replicate frame 0"
 
 
-@pytest.mark.parametrize("C,temporal,F_,H,W", [(256, 0, 3, 6, 10), (512, 1, 3, 4, 6), (512, 1, 1, 4, 6)])
+@pytest.mark.parametrize("C,temporal,F_,H,W", [(256, 0, 3, 6, 10), (512, 1, 3, 4, 6), (512, 1, 1, 4, 6),
+                                                # W % 32 == 0: the TMA shuffle-store path (incl. a ragged last m-tile)
+                                                (256, 0, 2, 5, 32), (512, 1, 3, 3, 64), (256, 1, 2, 7, 96)])
 def test_upsample_shuffle(svr2lib, C, temporal, F_, H, W):
     z = 2 if temporal else 1
     r = 4 * z

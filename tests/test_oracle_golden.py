@@ -6,8 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import dit_oracle, vae_oracle
-from oracle.make_golden import DIT_CASES, VAE_CASES, dit_inputs
+from oracle import color_oracle, dit_oracle, vae_oracle
+from oracle.make_golden import COLOR_CASES, DIT_CASES, VAE_CASES, color_inputs, dit_inputs
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -58,3 +58,31 @@ def test_bf16_mode_is_close_to_fp32(pkg):
     b = dit_oracle.dit_forward(sd, cfg, vid, txt, T, H, W, mode="ref_bf16").float()
     psnr = 10 * torch.log10(a.abs().max() ** 2 / (a - b).pow(2).mean())
     assert psnr > 45
+
+
+@pytest.mark.parametrize("name", list(COLOR_CASES))
+def test_color_oracle_matches_reference_golden(name):
+    """src/utils/color_fix.py goldens: wavelet and AdaIN bit for bit; LAB up to the tie order of the reference's
+    unstable torch.sort (a tied element may receive the adjacent reference value)."""
+    T, H, W = COLOR_CASES[name]
+    content, style = color_inputs(T, H, W)
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    assert torch.equal(color_oracle.wavelet_reconstruction(content, style), torch.from_numpy(g["wavelet"]))
+    assert torch.equal(color_oracle.adaptive_instance_normalization(content, style), torch.from_numpy(g["adain"]))
+    lab, ref = color_oracle.lab_color_transfer(content, style), torch.from_numpy(g["lab"])
+    assert (lab == ref).float().mean() > 0.99
+    assert 10 * torch.log10(4.0 / ((lab - ref) ** 2).mean()) > 60.0
+
+
+def test_color_oracle_properties():
+    """Histogram matching is an exact rank mapping; the wavelet split is a partition of the image."""
+    g = torch.Generator().manual_seed(1)
+    src, ref = torch.randn(5000, generator=g), torch.randn(5000, generator=g) * 3 + 1
+    out = color_oracle.histogram_match(src, ref)
+    assert torch.equal(out.sort().values, ref.sort().values)
+    assert torch.equal(out.argsort(stable=True), src.argsort(stable=True))
+    x = torch.rand(1, 3, 64, 80, generator=g) * 2 - 1
+    high, low = color_oracle.wavelet_decomposition(x, mode="fp32")
+    assert (high + low - x).abs().max() < 1e-5
+    img = color_oracle.sample_to_image(torch.tensor([-2.0, -1.0, 0.0, 0.5, 3.0]).view(1, 1, 1, 5).expand(1, 3, 1, 5))
+    assert img.shape == (1, 1, 5, 3) and torch.equal(img[0, 0, :, 0], torch.tensor([0.0, 0.0, 0.5, 0.75, 1.0]))

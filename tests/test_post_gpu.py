@@ -1,0 +1,118 @@
+"""-m gpu: post-decode colour correction + image formatting (csrc/post.cu through the C ABI and the
+``color_fix`` host mirror) against the goldens produced by the reference's src/utils/color_fix.py and
+against the oracle at larger sizes.  Tolerances are stated per test."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import color_oracle
+from oracle.make_golden import COLOR_CASES, color_inputs
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def cf(pkg):
+    return importlib.import_module("comfyui_seedvr2_videoupscaler_b200.color_fix")
+
+
+def psnr(a, b, peak=2.0):
+    mse = ((a.float().cpu() - b.float().cpu()) ** 2).mean().item()
+    return 99.0 if mse == 0 else 10 * np.log10(peak * peak / mse)
+
+
+def frac_equal(a, b):
+    return (a.float().cpu() == b.float().cpu()).float().mean().item()
+
+
+@pytest.mark.parametrize("name", list(COLOR_CASES))
+def test_color_fix_vs_reference_golden(cf, name):
+    T, H, W = COLOR_CASES[name]
+    content, style = color_inputs(T, H, W)
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    c, s = content.cuda(), style.cuda()
+    # wavelet: the 9-tap sum is order-independent up to the last fp32 bit -> bit-exact except (rarely) a 1-ulp bf16 tie
+    w = cf.wavelet_reconstruction(c, s)
+    ref = torch.from_numpy(g["wavelet"])
+    assert w.dtype == torch.bfloat16 and frac_equal(w, ref) > 0.999 and psnr(w, ref) > 80.0
+    # AdaIN: statistics in fp64 instead of torch's fp32 reduction; the bf16-rounded mean/std agree
+    a = cf.adaptive_instance_normalization(c, s)
+    ref = torch.from_numpy(g["adain"])
+    assert frac_equal(a, ref) > 0.99 and psnr(a, ref) > 60.0
+    # LAB: rank mapping; ties and 1e-7-level LAB differences move single elements to a neighbouring rank
+    l = cf.lab_color_transfer(c, s, None, luminance_weight=0.8)
+    ref = torch.from_numpy(g["lab"])
+    assert frac_equal(l, ref) > 0.98 and psnr(l, ref) > 55.0, (frac_equal(l, ref), psnr(l, ref))
+
+
+def test_color_fix_medium_size_vs_oracle(cf):
+    """A 2 x 270 x 480 clip (latent size of the 4K shard): all five dilations un-capped."""
+    content, style = color_inputs(2, 270, 480, seed=11)
+    c, s = content.cuda(), style.cuda()
+    w = cf.wavelet_reconstruction(c, s)
+    assert frac_equal(w, color_oracle.wavelet_reconstruction(content, style)) > 0.999
+    a = cf.adaptive_instance_normalization(c, s)
+    assert psnr(a, color_oracle.adaptive_instance_normalization(content, style)) > 60.0
+    l = cf.lab_color_transfer(c, s, None)
+    lo = color_oracle.lab_color_transfer(content, style)
+    assert psnr(l, lo) > 55.0 and frac_equal(l, lo) > 0.98
+    # luminance_weight = 1 keeps the content L* (color_fix.py:340-342)
+    l1 = cf.lab_color_transfer(c, s, None, luminance_weight=1.0)
+    assert psnr(l1, color_oracle.lab_color_transfer(content, style, luminance_weight=1.0)) > 55.0
+
+
+def test_histogram_match_is_exact_rank_mapping(svr2lib):
+    """Size-independent properties at 4M elements: the output is a permutation of the reference values and
+    preserves the order of the source."""
+    n = 1 << 22
+    g = torch.Generator().manual_seed(3)
+    src = torch.randn(n, generator=g).cuda()
+    ref = (torch.randn(n, generator=g) * 3 + 1).cuda()
+    out = torch.empty_like(src)
+    need = svr2lib.load().svr2_histogram_match_scratch_bytes(n)
+    scratch = torch.empty(need, device="cuda", dtype=torch.uint8)
+    svr2lib.call("svr2_histogram_match_f32", svr2lib.ptr(src), svr2lib.ptr(ref), svr2lib.ptr(out), n,
+                 svr2lib.ptr(scratch), need, svr2lib.stream())
+    assert torch.equal(out.sort().values, ref.sort().values)
+    order = src.argsort()
+    assert (out[order][1:] >= out[order][:-1]).all()
+    # too-small scratch is an error, not a crash
+    rc = svr2lib.load().svr2_histogram_match_f32(svr2lib.ptr(src), svr2lib.ptr(ref), svr2lib.ptr(out), n,
+                                                  svr2lib.ptr(scratch), 16, svr2lib.stream())
+    assert rc != 0 and b"scratch" in svr2lib.load().svr2_last_error()
+
+
+def test_lab_round_trip_and_image_format(cf, svr2lib):
+    """rgb -> LAB -> rgb is the identity up to bf16 rounding; sample_to_image equals the oracle bit for bit."""
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(2, 3, 33, 47, generator=g) * 2 - 1).to(torch.bfloat16)
+    xc = x.cuda()
+    n, hw = 2 * 33 * 47, 33 * 47
+    lab = torch.empty(3, n, device="cuda", dtype=torch.float32)
+    svr2lib.call("svr2_rgb_to_lab_f32", svr2lib.ptr(xc), svr2lib.ptr(lab), 2, hw, svr2lib.stream())
+    ref_lab = color_oracle.rgb_to_lab(((x.float() + 1) * 0.5).clamp(0, 1)).permute(1, 0, 2, 3).reshape(3, n)
+    assert (lab.cpu() - ref_lab).abs().max() < 2e-3          # L in [0,100], a/b in [-128,127]; fp32 pow differences
+    back = torch.empty_like(xc)
+    svr2lib.call("svr2_lab_to_rgb_bf16", svr2lib.ptr(lab[0]), None, svr2lib.ptr(lab[1]), svr2lib.ptr(lab[2]), 1.0,
+                 svr2lib.ptr(back), 2, hw, svr2lib.stream())
+    assert (back.float().cpu() - x.float()).abs().max() <= 2 ** -7      # one bf16 ulp near 1
+    y = torch.cat([x, torch.tensor([-3.0, 2.0, 0.3]).view(1, 3, 1, 1).expand(1, 3, 33, 47).to(torch.bfloat16)])
+    img = cf.sample_to_image(y.cuda())
+    assert img.shape == (3, 33, 47, 3) and torch.equal(img.float().cpu(), color_oracle.sample_to_image(y))
+
+
+def test_color_correction_switch(cf):
+    content, style = color_inputs(1, 40, 56)
+    c, s = content.cuda(), style.cuda()
+    assert torch.equal(cf.apply_color_correction(c, s, "none"), c)
+    assert torch.equal(cf.apply_color_correction(c, s, "wavelet"), cf.wavelet_reconstruction(c, s))
+    with pytest.raises(NotImplementedError):
+        cf.apply_color_correction(c, s, "hsv")
+    with pytest.raises(NotImplementedError):
+        cf.wavelet_reconstruction(c, s[:, :, :20])
+    with pytest.raises(Exception):
+        cf.wavelet_reconstruction(content, style)      # CPU tensors: no fallback
