@@ -163,6 +163,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--source", default="lowres", choices=["lowres", "target"],
+                    help="lowres: the clip enters at its source resolution (H/3 x W/3 for 720p->4K, H/2 x W/2 for "
+                         "540p->1080p) and is resized on the device by the pre-processing kernel, as in the "
+                         "reference pipeline; target: frames already at the target resolution")
+    ap.add_argument("--color_correction", default="none", choices=["none", "lab", "wavelet", "adain"],
+                    help="post-decode colour correction inside the step (reference CLI default: lab); the headline "
+                         "metric is quoted with 'none' = the north_star path (encode + DiT + decode)")
     ap.add_argument("--phases", action="store_true", help="print a per-kernel breakdown to stderr")
     ap.add_argument("--detail", action="store_true", help="with --phases: break GEMM/conv launches down by shape")
     args = ap.parse_args()
@@ -188,7 +195,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     eng = pipeline.build_synthetic_engine("3b", device=dev)
-    frames_host = synth_frames(frames_real, H, W, seed=42 + rank).to(torch.bfloat16).pin_memory()
+    # source clip: 720p for the 4K shard (x3), 540p for 1080p (x2), half size otherwise
+    div = 1 if args.source == "target" else (3 if H == 2160 else 2)
+    frames_host = synth_frames(frames_real, H // div, W // div, seed=42 + rank).to(torch.bfloat16).pin_memory()
     frames_dev = frames_host.to(dev)
     out_host = torch.empty(frames_real, H, W, 3, dtype=torch.bfloat16).pin_memory()
     gather_buf = torch.empty(world, frames_real, H, W, 3, device=dev, dtype=torch.bfloat16) if world > 1 else None
@@ -196,7 +205,7 @@ def main():
     noise = None
 
     def step(src):
-        y = eng.upscale_clip(src, noise=noise, seed=42)
+        y = eng.upscale_clip(src, noise=noise, seed=42, color_correction=args.color_correction, resolution=H)
         if world > 1:
             dist.all_gather_into_tensor(gather_buf.view(-1), y.reshape(-1).contiguous())
         return y
@@ -293,12 +302,13 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": desc, "frames_per_gpu": frames_real, "frames_padded": frames_pad, "resolution": [H, W],
-                   "parallelism": f"clip-dp{world}", "l2": "inputs/activations per step (>10 GB) exceed L2; no flush needed",
+                   "parallelism": f"clip-dp{world}", "color_correction": args.color_correction,
+                   "source_resolution": [H // div, W // div], "l2": "inputs/activations per step (>10 GB) exceed L2; no flush needed",
                    "weights": "random init, reference key layout, fp16 checkpoint -> bf16 compute",
                    "model_flops_per_clip": fm["dit"] + fm["enc"] + fm["dec"]},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frames_host.numel() * 2,
                 "d2h_bytes_per_step": out_host.numel() * 2,
-                "note": "SeedVR2Engine.upscale_clip on pinned host frames at target resolution; result copied back to host"},
+                "note": "SeedVR2Engine.upscale_clip on pinned host frames at the source resolution (resized on the device); result copied back to host"},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (Linear + implicit-GEMM Conv3d + upsample)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,

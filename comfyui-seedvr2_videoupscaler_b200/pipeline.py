@@ -6,7 +6,8 @@ Mirrors ``VideoDiffusionInfer`` (reference ``src/core/infer.py``): ``vae_encode`
 between phases on the device (no host bounce).  ``upscale_clip`` strings them
 together the way ``generation_phases.py`` does for one clip: 4n+1 temporal pad
 (:109-124), clamp + pad-16 + normalise (``generation_utils.py:72-84``), encode,
-condition = [latent | 1] (``infer.py:54-78``), DiT, decode, crop, [0,1].
+condition = [latent | 1] (``infer.py:54-78``), DiT, decode, crop, optional colour
+correction against the input clip (``generation_phases.py:1249-1319``), [0,1] image format.
 """
 from __future__ import annotations
 
@@ -14,6 +15,7 @@ from typing import Dict, Optional
 
 import torch
 
+from . import color_fix, preprocess
 from .dit import B200NaDiT, dit_config
 from .vae import B200VideoVAE
 
@@ -62,27 +64,35 @@ class SeedVR2Engine:
 
     # ---- one clip end to end ------------------------------------------------
     @torch.no_grad()
-    def upscale_clip(self, frames: torch.Tensor, noise: Optional[torch.Tensor] = None, seed: int = 42) -> torch.Tensor:
-        """frames (T,H,W,3) in [0,1], already resized to the target resolution.
-        Returns (T,H,W,3) bf16 in [0,1] on the device."""
-        T0, H0, W0, _ = frames.shape
-        x = frames.to(self.device, torch.bfloat16).clamp(0, 1)
+    def upscale_clip(self, frames: torch.Tensor, noise: Optional[torch.Tensor] = None, seed: int = 42,
+                     color_correction: str = "none", resolution: Optional[int] = None,
+                     max_resolution: int = 0) -> torch.Tensor:
+        """frames (T,h,w,3) in [0,1]; ``resolution`` = target shortest edge (None: keep the size, i.e. the frames
+        are already at the target resolution).  Returns (T,H,W,3) bf16 in [0,1] on the device.
+        ``color_correction``: "none", "lab" (the reference CLI default), "wavelet" or "adain" — matched against the
+        transformed input clip (generation_phases.py:1299-1317)."""
+        T0 = frames.shape[0]
+        x = frames.to(self.device)
         T = pad_4n1(T0)
         if T > T0:
             x = torch.cat([x, x[-1:].expand(T - T0, -1, -1, -1)], 0)
-        ph, pw = (16 - H0 % 16) % 16, (16 - W0 % 16) % 16
-        x = x.permute(3, 0, 1, 2)                                  # c t h w
-        if ph or pw:
-            x = torch.nn.functional.pad(x, (0, pw, 0, ph))
-        x = (x - 0.5) / 0.5
+        # resize (identity when the frames already have the target size) + clamp + pad-16 + normalise + c t h w
+        # in one kernel (prepare_video_transforms, generation_utils.py:72-84)
+        res = resolution if resolution is not None else min(frames.shape[1], frames.shape[2])
+        tf = preprocess.VideoTransform(res, max_resolution)
+        H0, W0 = tf.true_size(frames.shape[1], frames.shape[2])
+        x = tf.run(x, channels_last=True)                          # (3, T, Hp, Wp) bf16 in [-1,1]
         latent = self.vae_encode(x)
         if noise is None:
             g = torch.Generator(device=self.device).manual_seed(seed)
             noise = torch.randn(latent.shape, generator=g, device=self.device, dtype=torch.bfloat16)
         x0 = self.inference(noise, latent)
         y = self.vae_decode(x0)                                     # (3,T,H,W)
-        y = y[:, :T0, :H0, :W0].permute(1, 2, 3, 0)
-        return (y.float() * 0.5 + 0.5).clamp(0, 1).to(torch.bfloat16)
+        sample = y[:, :T0, :H0, :W0].permute(1, 0, 2, 3)            # t c h w, the layout of phase 4
+        if color_correction != "none":
+            style = x[:, :T0, :H0, :W0].permute(1, 0, 2, 3)        # the transformed input clip in [-1,1]
+            sample = color_fix.apply_color_correction(sample, style, color_correction)
+        return color_fix.sample_to_image(sample)                    # t h w c in [0,1]
 
 
 def build_synthetic_engine(variant="3b", device="cuda", seed=1234, txt_len=58) -> SeedVR2Engine:

@@ -172,6 +172,17 @@ int svr2_histogram_match_f32(const float* source, const float* reference, float*
  * clamp(-1,1) * 0.5 + 0.5 */
 int svr2_sample_to_image_bf16(const void* sample, void* image, int frames, int64_t hw, void* stream);
 
+/* ---- Clip pre-processing (prepare_video_transforms, src/core/generation_utils.py:72-84).
+ * Antialiased bicubic resize (torchvision resize -> torch _upsample_bicubic2d_aa semantics, fp32 accumulation, result
+ * rounded to bf16) of frames given as [T,h,w,cin] (channels_last != 0, first 3 channels) or [T,3,h,w]; in_dtype
+ * 0 fp32 | 1 bf16 | 2 fp16, values rounded to bf16 on load (the pipeline's compute dtype).
+ *   finish == 0: out [T,3,H,W] bf16 (plain resize);
+ *   finish != 0: out [3,T,Hp,Wp] bf16 = clamp(0,1) -> zero pad to multiples of 16 -> (x - 0.5) / 0.5 -> c t h w,
+ *                Hp = ceil16(H), Wp = ceil16(W)  (what VideoDiffusionInfer.vae_encode consumes). */
+int64_t svr2_resize_scratch_bytes(int h, int w, int H, int W);
+int svr2_resize_bicubic_aa_bf16(const void* in, int in_dtype, int channels_last, int cin, int frames, int h, int w,
+                                void* out, int H, int W, int finish, void* scratch, int64_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

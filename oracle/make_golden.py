@@ -194,14 +194,58 @@ def run_color_cases():
                             **{k: v.float().numpy().astype(np.float32) for k, v in outs.items()})
 
 
+# ---- clip pre-processing (prepare_video_transforms): name -> (T, h, w, resolution, max_resolution)
+PRE_CASES = {
+    "pre_up3x": (2, 30, 41, 90, 0),              # 3x up-scale, odd sizes, pad 90x123 -> 96x128
+    "pre_up_landscape": (1, 45, 80, 72, 0),
+    "pre_down": (2, 64, 48, 40, 0),              # down-scale: the antialias support widens
+    "pre_capped": (1, 36, 64, 108, 160),         # max_resolution triggers the second resize
+    "pre_identity": (2, 33, 57, 33, 0),          # already at the target size
+}
+
+
+def pre_inputs(T, h, w, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(T, h, w, 3, generator=g) * 1.1 - 0.05     # [T,h,w,3], slightly outside [0,1]
+
+
+def run_pre_cases():
+    """The reference's own transform classes composed as prepare_video_transforms does
+    (src/core/generation_utils.py:72-84), run on CPU on the bf16 clip (generation_phases.py:380-413)."""
+    import importlib
+    if ref_import.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, ref_import.REFERENCE_ROOT)
+    na = importlib.import_module("src.data.image.transforms.na_resize")
+    dc = importlib.import_module("src.data.image.transforms.divisible_crop")
+    from torchvision.transforms import Compose, Lambda, Normalize
+    from oracle import pre_oracle
+
+    for name, (T, h, w, res, mx) in PRE_CASES.items():
+        tf = Compose([na.NaResize(resolution=res, mode="side", downsample_only=False, max_resolution=mx),
+                      Lambda(lambda x: torch.clamp(x, 0.0, 1.0)), dc.DivisiblePad((16, 16)), Normalize(0.5, 0.5),
+                      Lambda(lambda x: x.permute(1, 0, 2, 3))])
+        frames = pre_inputs(T, h, w)
+        ref = tf(frames.to(torch.bfloat16).permute(0, 3, 1, 2))
+        assert ref.dtype == torch.bfloat16
+        ora = pre_oracle.preprocess(frames, res, mx)
+        d = (ref.float() - ora).abs()
+        same = (d == 0).float().mean().item()
+        assert ref.shape == ora.shape and same > 0.999 and d.max().item() <= 2 ** -7, (name, same, d.max().item())
+        print(f"{name}: {tuple(ref.shape)} oracle vs reference transform {100 * same:.3f}% bit-equal, max {d.max().item():.4f}")
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), out=ref.float().numpy().astype(np.float32))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
-    if "--color-only" not in sys.argv:
+    if "--color-only" not in sys.argv and "--pre-only" not in sys.argv:
         for name in DIT_CASES:
             run_dit_case(name)
         run_vae_cases()
-    run_color_cases()
+    if "--pre-only" not in sys.argv:
+        run_color_cases()
+    if "--color-only" not in sys.argv:
+        run_pre_cases()
 
 
 if __name__ == "__main__":

@@ -6,8 +6,9 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import color_oracle, dit_oracle, vae_oracle
-from oracle.make_golden import COLOR_CASES, DIT_CASES, VAE_CASES, color_inputs, dit_inputs
+from oracle import color_oracle, dit_oracle, pre_oracle, vae_oracle
+from oracle.make_golden import (COLOR_CASES, DIT_CASES, PRE_CASES, VAE_CASES, color_inputs, dit_inputs,
+                                pre_inputs)
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -86,3 +87,26 @@ def test_color_oracle_properties():
     assert (high + low - x).abs().max() < 1e-5
     img = color_oracle.sample_to_image(torch.tensor([-2.0, -1.0, 0.0, 0.5, 3.0]).view(1, 1, 1, 5).expand(1, 3, 1, 5))
     assert img.shape == (1, 1, 5, 3) and torch.equal(img[0, 0, :, 0], torch.tensor([0.0, 0.0, 0.5, 0.75, 1.0]))
+
+
+@pytest.mark.parametrize("name", list(PRE_CASES))
+def test_pre_oracle_matches_reference_golden(name):
+    """prepare_video_transforms goldens (reference transform classes on CPU): bit-equal except where the fp32
+    accumulation order flips a bf16 rounding (at most one ulp)."""
+    T, h, w, res, mx = PRE_CASES[name]
+    ref = torch.from_numpy(np.load(os.path.join(GOLD, name + ".npz"))["out"])
+    out = pre_oracle.preprocess(pre_inputs(T, h, w), res, mx)
+    assert out.shape == ref.shape
+    d = (out - ref).abs()
+    assert (d == 0).float().mean() > 0.999 and d.max() <= 2 ** -7
+
+
+def test_pre_oracle_sizes_and_weights():
+    assert pre_oracle.resized_size(720, 1280, 2160) == ((2160, 3840), False)
+    assert pre_oracle.resized_size(1280, 720, 1080) == ((1920, 1080), False)
+    assert pre_oracle.resized_size(540, 960, 1080, 1600) == ((900, 1600), True)
+    first, count, w = pre_oracle.aa_weights(96, 40)          # 2.4x down-scale: the support widens to 4.8 taps
+    assert count.max() >= 9 and np.allclose(w.sum(1), 1.0, atol=1e-6)
+    assert pre_oracle.aa_weights(30, 90)[1].max() <= 5       # up-scale: plain 4-tap cubic (+1 zero-weight tap)
+    first, count, w = pre_oracle.aa_weights(33, 33)          # identity: a single unit tap
+    assert np.allclose(np.sort(w, 1)[:, -1], 1.0) and np.allclose(np.abs(w).sum(1), 1.0)
