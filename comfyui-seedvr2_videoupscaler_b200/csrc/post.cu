@@ -214,6 +214,29 @@ __global__ void __launch_bounds__(256) sample_to_image_kernel(const __nv_bfloat1
   }
 }
 
+// Temporal-overlap cross-fade (blend_overlapping_frames, generation_utils.py:284-312):
+// out = rn(rn(prev * w_prev[f]) + rn(cur * w_cur[f])), frames of `frame_elems` bf16 values, 8 per thread
+__global__ void __launch_bounds__(256) blend_overlap_kernel(const uint4* __restrict__ prev, const uint4* __restrict__ cur,
+                                                            uint4* __restrict__ out, const float* __restrict__ w_prev,
+                                                            const float* __restrict__ w_cur, long long vec_per_frame) {
+  const int f = blockIdx.y;
+  const float wp = w_prev[f], wc = w_cur[f];
+  const long long base = (long long)f * vec_per_frame;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < vec_per_frame; i += (long long)gridDim.x * 256) {
+    const uint4 a = prev[base + i], b = cur[base + i];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float lo = rn(__uint_as_float(aw[e] << 16) * wp) + rn(__uint_as_float(bw[e] << 16) * wc);
+      const float hi = rn(__uint_as_float(aw[e] & 0xffff0000u) * wp) + rn(__uint_as_float(bw[e] & 0xffff0000u) * wc);
+      const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+      o[e] = *reinterpret_cast<const uint32_t*>(&pk);
+    }
+    out[base + i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 inline int grid_for(long long n, int per_block = 256, int waves = 16) {
   long long b = (n + per_block - 1) / per_block;
   const long long cap = (long long)num_sms() * waves;
@@ -324,4 +347,17 @@ extern "C" int svr2_sample_to_image_bf16(const void* sample, void* image, int fr
   sample_to_image_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)sample,
                                                                             (__nv_bfloat16*)image, hw, total);
   return check_launch("sample_to_image");
+}
+
+extern "C" int svr2_blend_overlap_bf16(const void* prev_tail, const void* cur_head, void* out, const float* w_prev,
+                                       const float* w_cur, int overlap, int64_t frame_elems, void* stream) {
+  if (overlap <= 0 || frame_elems <= 0) return set_error(SVR2_ERR_ARG, "svr2_blend_overlap_bf16: empty input");
+  if (frame_elems % 8) return set_error(SVR2_ERR_ARG, "svr2_blend_overlap_bf16: frame_elems must be a multiple of 8");
+  if (overlap > 65535) return set_error(SVR2_ERR_ARG, "svr2_blend_overlap_bf16: overlap <= 65535");
+  const long long vec = frame_elems / 8;
+  int bx = grid_for(vec, 256, 8) / overlap;
+  if (bx < 1) bx = 1;
+  blend_overlap_kernel<<<dim3(bx, overlap), 256, 0, (cudaStream_t)stream>>>((const uint4*)prev_tail, (const uint4*)cur_head,
+                                                                             (uint4*)out, w_prev, w_cur, vec);
+  return check_launch("blend_overlap");
 }

@@ -106,3 +106,17 @@ def build_synthetic_engine(variant="3b", device="cuda", seed=1234, txt_len=58) -
     eng = SeedVR2Engine(cfg, dit_sd, vae_sd, txt, device=device)
     del dit_sd, vae_sd
     return eng
+
+
+def build_engine(dit_checkpoint: str, vae_checkpoint: str, txt_embed, device="cuda") -> SeedVR2Engine:
+    """Engine from checkpoint files: DiT ``seedvr2_ema_{3b,7b}_{fp16,fp8_e4m3fn}.safetensors``, VAE
+    ``ema_vae_fp16.safetensors`` (``model_registry.py:40-75``) and the positive text embedding (``pos_emb.pt``,
+    ``generation_utils.py:load_text_embeddings``) given as a path or tensor."""
+    from . import weights
+    dit_sd = weights.load_state_dict(dit_checkpoint)
+    cfg = dit_config(weights.detect_dit_variant(dit_sd))
+    vae_sd = weights.load_state_dict(vae_checkpoint)
+    txt = torch.load(txt_embed, map_location="cpu", weights_only=True) if isinstance(txt_embed, str) else txt_embed
+    if txt.ndim == 3:
+        txt = txt[0]
+    return SeedVR2Engine(cfg, dit_sd, vae_sd, txt, device=device)

@@ -45,9 +45,33 @@ def gather_frames(local: torch.Tensor, counts: List[int], group=None) -> torch.T
     return torch.cat([out[r, :counts[r]] for r in range(world)], 0)
 
 
+def blend_weights(overlap: int, dtype=torch.bfloat16):
+    """Per-frame (w_prev, w_cur) of blend_overlapping_frames (generation_utils.py:299-310), computed with the same
+    torch ops in the frames' dtype so that every rounding point matches: Hann cross-fade over the middle third for
+    overlap >= 3, linear below."""
+    if overlap >= 3:
+        t = torch.linspace(0.0, 1.0, steps=overlap, dtype=dtype)
+        blend_start, blend_end = 1.0 / 3.0, 2.0 / 3.0
+        u = ((t - blend_start) / (blend_end - blend_start)).clamp(0.0, 1.0)
+        w_prev = 0.5 + 0.5 * torch.cos(torch.pi * u)
+    else:
+        w_prev = torch.linspace(1.0, 0.0, steps=overlap, dtype=dtype)
+    return w_prev, 1.0 - w_prev
+
+
 def blend_overlap(prev_tail: torch.Tensor, cur_head: torch.Tensor) -> torch.Tensor:
-    """Linear cross-fade of the overlapping frames of two neighbouring ranges
-    (generation_utils.py:284-312 uses a Hann/linear window; linear here)."""
+    """Cross-fade of the ``overlap`` frames two neighbouring ranges share (``blend_overlapping_frames``,
+    generation_utils.py:284-312): [overlap, H, W, C] bf16 each, on the GPU (one libsvr2 kernel)."""
+    from . import lib
+    assert prev_tail.shape == cur_head.shape and prev_tail.is_cuda
     n = prev_tail.shape[0]
-    w = torch.linspace(0, 1, n + 2, device=prev_tail.device, dtype=torch.float32)[1:-1].view(n, 1, 1, 1)
-    return (prev_tail.float() * (1 - w) + cur_head.float() * w).to(prev_tail.dtype)
+    a, b = prev_tail.to(torch.bfloat16).contiguous(), cur_head.to(torch.bfloat16).contiguous()
+    w_prev, w_cur = blend_weights(n, torch.bfloat16)
+    wp, wc = w_prev.float().to(a.device), w_cur.float().to(a.device)
+    elems = a[0].numel()
+    if elems % 8:
+        raise ValueError("frames must hold a multiple of 8 values")
+    out = torch.empty_like(a)
+    lib.call("svr2_blend_overlap_bf16", lib.ptr(a), lib.ptr(b), lib.ptr(out), lib.ptr(wp), lib.ptr(wc), n, elems,
+             lib.stream(), nbytes=6.0 * a.numel())
+    return out

@@ -167,3 +167,39 @@ def synth_vae_state_dict(seed: int = 4321, dtype=torch.float16, device="cpu",
     m.norm("decoder.conv_norm_out", rc[-1])
     m.conv("decoder.conv_out", 3, rc[-1], gain=0.5)
     return m.sd
+
+
+# ----------------------------------------------------------------------------------------------------------
+# checkpoint files
+def load_state_dict(path: str, device="cpu") -> Dict[str, torch.Tensor]:
+    """Checkpoint file -> state dict with the reference key layout (``load_quantized_state_dict``,
+    ``src/core/model_loader.py:84-153``): ``.safetensors`` in fp16 / bf16 / fp32 or fp8_e4m3fn storage (the CLI default
+    model is ``*_fp8_e4m3fn.safetensors``, ``model_registry.py:56``) and ``.pth`` / ``.pt``.  The engines cast every
+    tensor to their bf16 / fp32 layouts on the GPU, so fp8 and fp16 storage need no separate path.  GGUF (block-quantised)
+    checkpoints are not part of the B200 path."""
+    low = path.lower()
+    if low.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        sd = load_file(path, device=str(device))
+    elif low.endswith((".pth", ".pt")):
+        sd = torch.load(path, map_location=device, weights_only=True)
+        if isinstance(sd, dict) and "state_dict" in sd and all(not torch.is_tensor(v) for v in sd.values()):
+            sd = sd["state_dict"]
+    elif low.endswith(".gguf"):
+        raise NotImplementedError("GGUF checkpoints are not supported by the B200 engine (use the safetensors files)")
+    else:
+        raise ValueError(f"unknown checkpoint format: {path}")
+    prefix = "model.diffusion_model."          # ComfyUI-style exports (model_loader.py:143-147)
+    if any(k.startswith(prefix) for k in sd):
+        sd = {(k[len(prefix):] if k.startswith(prefix) else k): v for k, v in sd.items()}
+    return sd
+
+
+def detect_dit_variant(sd: Dict[str, torch.Tensor]) -> str:
+    """3B (dim 2560, 32 layers) or 7B (dim 3072, 36 layers) from the checkpoint itself."""
+    dim = sd["vid_in.proj.weight"].shape[0]
+    if dim == 2560:
+        return "3b"
+    if dim == 3072:
+        return "7b"
+    raise ValueError(f"unrecognised NaDiT width {dim}")

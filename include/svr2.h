@@ -172,6 +172,12 @@ int svr2_histogram_match_f32(const float* source, const float* reference, float*
  * clamp(-1,1) * 0.5 + 0.5 */
 int svr2_sample_to_image_bf16(const void* sample, void* image, int frames, int64_t hw, void* stream);
 
+/* Temporal-overlap cross-fade of two neighbouring frame ranges (blend_overlapping_frames,
+ * src/core/generation_utils.py:284-312): out[f] = bf16(bf16(prev[f] * w_prev[f]) + bf16(cur[f] * w_cur[f])); the
+ * per-frame weights (Hann window for overlap >= 3, linear below) are passed as device fp32 arrays of bf16 values. */
+int svr2_blend_overlap_bf16(const void* prev_tail, const void* cur_head, void* out, const float* w_prev,
+                            const float* w_cur, int overlap, int64_t frame_elems, void* stream);
+
 /* ---- Clip pre-processing (prepare_video_transforms, src/core/generation_utils.py:72-84).
  * Antialiased bicubic resize (torchvision resize -> torch _upsample_bicubic2d_aa semantics, fp32 accumulation, result
  * rounded to bf16) of frames given as [T,h,w,cin] (channels_last != 0, first 3 channels) or [T,3,h,w]; in_dtype

@@ -164,3 +164,19 @@ def sample_to_image(sample: torch.Tensor, mode: str = "ref_bf16") -> torch.Tenso
     """generation_phases.py:1322-1345: [T,C,H,W] in [-1,1] -> [T,H,W,C] in [0,1]."""
     x = _r(sample.float(), mode).permute(0, 2, 3, 1)
     return _r(_r(x.clamp(-1.0, 1.0) * 0.5, mode) + 0.5, mode).contiguous()
+
+
+def blend_overlapping_frames(prev_tail: torch.Tensor, cur_head: torch.Tensor, overlap: int) -> torch.Tensor:
+    """generation_utils.py:284-312 on bf16 frames [overlap, H, W, C]: Hann cross-fade over the middle third for
+    overlap >= 3, linear below; weights and products carry the frames' dtype (every op rounds to bf16)."""
+    dt = torch.bfloat16
+    if overlap >= 3:
+        t = torch.linspace(0.0, 1.0, steps=overlap, dtype=dt)
+        u = ((t - 1.0 / 3.0) / (2.0 / 3.0 - 1.0 / 3.0)).clamp(0.0, 1.0)
+        w_prev = 0.5 + 0.5 * torch.cos(torch.pi * u)
+    else:
+        w_prev = torch.linspace(1.0, 0.0, steps=overlap, dtype=dt)
+    w_prev = w_prev.view(overlap, 1, 1, 1)
+    w_cur = 1.0 - w_prev
+    a, b = prev_tail.to(dt), cur_head.to(dt)
+    return (a * w_prev + b * w_cur).float()

@@ -192,6 +192,22 @@ def run_color_cases():
         print(f"{name}: wavelet/adain oracle == reference (bit-exact); lab {100 * same:.2f}% equal, {psnr:.1f} dB")
         np.savez_compressed(os.path.join(GOLD, name + ".npz"),
                             **{k: v.float().numpy().astype(np.float32) for k, v in outs.items()})
+    # temporal-overlap cross-fade (src/core/generation_utils.py:284-312), bit for bit for every overlap length
+    gu_src = open(os.path.join(ref_import.REFERENCE_ROOT, "src/core/generation_utils.py")).read()
+    start = gu_src.index("def blend_overlapping_frames")
+    ns = {"torch": torch}
+    exec(gu_src[start:gu_src.index("\ndef ", start + 10)], ns)     # the function only (its module needs a GPU stack)
+    g = torch.Generator().manual_seed(21)
+    blends = {}
+    for ov in (1, 2, 3, 4, 7, 8):
+        a = torch.rand(ov, 6, 8, 3, generator=g).to(torch.bfloat16)
+        b = torch.rand(ov, 6, 8, 3, generator=g).to(torch.bfloat16)
+        ref_out = ns["blend_overlapping_frames"](a, b, ov)
+        assert ref_out.dtype == torch.bfloat16
+        assert torch.equal(ref_out.float(), co.blend_overlapping_frames(a, b, ov)), ov
+        blends[f"ov{ov}"] = ref_out.float().numpy().astype(np.float32)
+    print("blend_overlapping_frames: oracle == reference (bit-exact) for overlaps 1,2,3,4,7,8")
+    np.savez_compressed(os.path.join(GOLD, "blend_overlap.npz"), **blends)
 
 
 # ---- clip pre-processing (prepare_video_transforms): name -> (T, h, w, resolution, max_resolution)

@@ -115,3 +115,30 @@ def test_vae_slice_plan_matches_reference_split(pkg):
     for T, size in ((33, 8), (21, 4), (6, 1)):
         cuts = plan(T, size)
         assert cuts[0][0] == 0 and cuts[-1][1] == T and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+
+
+def test_checkpoint_loader_formats(pkg, tmp_path):
+    """weights.load_state_dict: safetensors in fp16 and fp8_e4m3fn storage, ComfyUI prefix stripping, .pth, GGUF refusal."""
+    from safetensors.torch import save_file
+    cfg = dit_oracle.dit_config("3b", layers=2, mm_layers=1, dim=256, heads=2)
+    sd = pkg.weights.synth_dit_state_dict(cfg, seed=3, dtype=torch.float16)
+    f16 = tmp_path / "dit_fp16.safetensors"
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(f16))
+    got = pkg.weights.load_state_dict(str(f16))
+    assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    f8 = tmp_path / "dit_fp8_e4m3fn.safetensors"
+    save_file({"model.diffusion_model." + k: (v.to(torch.float8_e4m3fn) if v.ndim == 2 else v).contiguous()
+               for k, v in sd.items()}, str(f8))
+    got8 = pkg.weights.load_state_dict(str(f8))
+    assert set(got8) == set(sd)
+    k2 = next(k for k, v in sd.items() if v.ndim == 2)
+    assert got8[k2].dtype == torch.float8_e4m3fn
+    assert torch.equal(got8[k2].to(torch.bfloat16), sd[k2].to(torch.float8_e4m3fn).to(torch.bfloat16))
+    pth = tmp_path / "vae.pth"
+    torch.save({"a.weight": torch.ones(2, 2)}, str(pth))
+    assert torch.equal(pkg.weights.load_state_dict(str(pth))["a.weight"], torch.ones(2, 2))
+    with pytest.raises(NotImplementedError):
+        pkg.weights.load_state_dict(str(tmp_path / "model.gguf"))
+    full = {"vid_in.proj.weight": torch.empty(2560, 132)}
+    assert pkg.weights.detect_dit_variant(full) == "3b"
+    assert pkg.weights.detect_dit_variant({"vid_in.proj.weight": torch.empty(3072, 132)}) == "7b"

@@ -43,6 +43,27 @@ def test_dit_vs_golden(pkg, name):
     assert torch.equal(out, out2)
 
 
+def test_dit_from_fp8_safetensors_file(pkg, tmp_path):
+    """A *_fp8_e4m3fn.safetensors checkpoint (the reference CLI's default model file) loads straight into the engine:
+    same output as the engine built from the de-quantised tensors, finite, close to the fp16 checkpoint's output."""
+    from safetensors.torch import save_file
+    dit = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.dit")
+    variant, over, (T, H, W), l = DIT_CASES["dit3b_tiny_t3"]
+    cfg = dit.dit_config(variant, **over)
+    sd = pkg.weights.synth_dit_state_dict(cfg, seed=1234, dtype=torch.float16)
+    path = str(tmp_path / "seedvr2_tiny_fp8_e4m3fn.safetensors")
+    save_file({k: (v.to(torch.float8_e4m3fn) if (v.ndim == 2 and "freqs" not in k) else v).contiguous()
+               for k, v in sd.items()}, path)
+    sd8 = pkg.weights.load_state_dict(path)
+    assert any(v.dtype == torch.float8_e4m3fn for v in sd8.values())
+    vid, txt = dit_inputs(cfg, T, H, W, l)
+    run = lambda d: dit.B200NaDiT(cfg, d)(vid.cuda(), txt.cuda(), [[T, H, W]], [[l]]).vid_sample
+    out8 = run(sd8)
+    out8_deq = run({k: (v.to(torch.float16) if v.dtype == torch.float8_e4m3fn else v) for k, v in sd8.items()})
+    assert torch.isfinite(out8).all() and torch.equal(out8, out8_deq)
+    assert psnr(out8, run(sd)) > 20.0          # fp8 storage costs precision, not sanity
+
+
 @pytest.fixture(scope="module")
 def vae_pair(pkg):
     vae = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.vae")

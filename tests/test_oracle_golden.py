@@ -110,3 +110,20 @@ def test_pre_oracle_sizes_and_weights():
     assert pre_oracle.aa_weights(30, 90)[1].max() <= 5       # up-scale: plain 4-tap cubic (+1 zero-weight tap)
     first, count, w = pre_oracle.aa_weights(33, 33)          # identity: a single unit tap
     assert np.allclose(np.sort(w, 1)[:, -1], 1.0) and np.allclose(np.abs(w).sum(1), 1.0)
+
+
+def test_blend_overlap_oracle_matches_reference_golden(pkg):
+    """blend_overlapping_frames (generation_utils.py:284-312): same inputs as oracle/make_golden.py, bit for bit;
+    the host-side weight table of shard.py is the same computation."""
+    import importlib
+    shard = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.shard")
+    gold = np.load(os.path.join(GOLD, "blend_overlap.npz"))
+    g = torch.Generator().manual_seed(21)
+    for ov in (1, 2, 3, 4, 7, 8):
+        a = torch.rand(ov, 6, 8, 3, generator=g).to(torch.bfloat16)
+        b = torch.rand(ov, 6, 8, 3, generator=g).to(torch.bfloat16)
+        out = color_oracle.blend_overlapping_frames(a, b, ov)
+        assert torch.equal(out, torch.from_numpy(gold[f"ov{ov}"]))
+        w_prev, w_cur = shard.blend_weights(ov)
+        ref = (a * w_prev.view(ov, 1, 1, 1) + b * w_cur.view(ov, 1, 1, 1)).float()
+        assert torch.equal(ref, out)

@@ -174,3 +174,19 @@ def test_preprocess_identity_size_and_padding(pre):
     ref = (frames.to(torch.bfloat16).float().clamp(0, 1) - 0.5).to(torch.bfloat16).float() / 0.5
     assert torch.equal(out[:, :, :72, :100].float(), ref.permute(3, 0, 1, 2))
     assert (out[:, :, 72:, :] == -1).all() and (out[:, :, :, 100:] == -1).all()
+
+
+def test_blend_overlap_vs_reference_golden(pkg):
+    """Temporal-overlap cross-fade kernel against the reference's blend_overlapping_frames goldens, bit for bit."""
+    shard = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.shard")
+    gold = np.load(os.path.join(GOLD, "blend_overlap.npz"))
+    g = torch.Generator().manual_seed(21)
+    for ov in (1, 2, 3, 4, 7, 8):
+        a = torch.rand(ov, 6, 8, 3, generator=g).to(torch.bfloat16)
+        b = torch.rand(ov, 6, 8, 3, generator=g).to(torch.bfloat16)
+        out = shard.blend_overlap(a.cuda(), b.cuda())
+        assert torch.equal(out.float().cpu(), torch.from_numpy(gold[f"ov{ov}"])), ov
+    # a 4K-sized pair of frames: same result as the oracle
+    a = torch.rand(3, 270, 480, 3, generator=g).to(torch.bfloat16)
+    b = torch.rand(3, 270, 480, 3, generator=g).to(torch.bfloat16)
+    assert torch.equal(shard.blend_overlap(a.cuda(), b.cuda()).float().cpu(), color_oracle.blend_overlapping_frames(a, b, 3))
