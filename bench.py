@@ -36,6 +36,9 @@ WORKLOADS = {
     # name: (real frames, H, W, description)
     "4k_shard": (8, 2160, 3840, "SeedVR2-3B bf16, 8-frame (->9) 720p->4K clip per GPU = BASELINE config 3 shard"),
     "1080p": (16, 1080, 1920, "SeedVR2-3B bf16, 16-frame (->17) 540p->1080p clip = BASELINE config 2"),
+    "4k_clip64": (64, 2160, 3840, "SeedVR2-3B bf16, 64-frame (->65) 720p->4K as ONE clip on one GPU = BASELINE config 3' "
+                                  "(17 latent frames, 2083-token windows, temporally sliced VAE)"),
+    "4k_shard_7b": (4, 2160, 3840, "SeedVR2-7B bf16, 4-frame (->5) 720p->4K clip per GPU = BASELINE config 4 shard"),
     "720p": (8, 720, 1280, "SeedVR2-3B bf16, 8-frame (->9) 360p->720p clip (smoke)"),
     "tiny": (4, 128, 192, "tiny clip (smoke)"),
 }
@@ -195,7 +198,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    eng = pipeline.build_synthetic_engine("3b", device=dev)
+    variant = "7b" if args.workload.endswith("_7b") else "3b"
+    eng = pipeline.build_synthetic_engine(variant, device=dev)
     # source clip: 720p for the 4K shard (x3), 540p for 1080p (x2), half size otherwise
     div = 1 if args.source == "target" else (3 if H == 2160 else 2)
     frames_host = synth_frames(frames_real, H // div, W // div, seed=42 + rank).to(torch.bfloat16).pin_memory()
@@ -275,7 +279,7 @@ def main():
     g_ms = sum(d["ms"] for n, d in prof.items() if is_gemm(n))
     g_calls = sum(d["calls"] for n, d in prof.items() if is_gemm(n))
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
-    fm = flop_model(frames_pad, H, W)
+    fm = flop_model(frames_pad, H, W, variant)
     # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of one representative
     # launch (profiles/ncu_full_r1.json, conv 256->256 3x3x3 at 2x1080x1920 on the CTA-pair kernel)
     traffic = None
@@ -298,7 +302,8 @@ def main():
         print(f"  sum of kernel time {tot / args.steps:.1f} ms/step vs step {ms / args.steps:.1f} ms; model FLOPs/clip "
               f"{(fm['dit'] + fm['enc'] + fm['dec']) / 1e15:.3f} PFLOP", file=sys.stderr)
     line = {
-        "metric": "upscaled frames/sec SeedVR2-3B 720p->4K" if args.workload == "4k_shard" else "upscaled frames/sec SeedVR2-3B",
+        "metric": ("upscaled frames/sec SeedVR2-3B 720p->4K" if args.workload == "4k_shard"
+                   else f"upscaled frames/sec SeedVR2-{variant.upper()}"),
         "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",

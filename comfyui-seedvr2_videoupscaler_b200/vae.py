@@ -285,11 +285,18 @@ class B200VideoVAE:
 
     # ---- temporal slice planning -------------------------------------------
     BYTES_PER_PIXEL_FRAME = 1500     # measured peak working set of one full-resolution frame (decode or encode)
+    # Slicing keeps, for every tensor that feeds a causal conv, the last two frames of the previous slice (the
+    # reference's per-conv `memory`).  Summed over the decoder that is 4.3 kB per full-resolution pixel and frame
+    # (1280 channels at full resolution, 2304 at 1/2, 3584 at 1/4, ~5200 at 1/8), 2.0 kB for the encoder.
+    DEC_STATE_BYTES_PER_PIXEL = 2 * 4400
+    ENC_STATE_BYTES_PER_PIXEL = 2 * 2100
 
-    def _frames_that_fit(self, H: int, W: int) -> int:
+    def _frames_that_fit(self, H: int, W: int, state_bytes_per_pixel: int = 0) -> int:
+        """Full-resolution frames one pass may hold, from the free HBM (minus the slicing state when slicing)."""
         free, _ = torch.cuda.mem_get_info(self.device)
         free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
-        return max(1, int(0.85 * free) // (self.BYTES_PER_PIXEL_FRAME * H * W))
+        budget = int(0.85 * free) - state_bytes_per_pixel * H * W
+        return max(1, budget // (self.BYTES_PER_PIXEL_FRAME * H * W))
 
     @staticmethod
     def _plan(T: int, size: int):
@@ -306,6 +313,8 @@ class B200VideoVAE:
         if len(cuts) == 1:
             return fn(src)
         outs = []
+        if not torch.cuda.is_current_stream_capturing():
+            torch.cuda.empty_cache()        # long clips run close to the HBM limit: start from an unfragmented pool
         self._chunk = {"first": True, "state": {}}
         try:
             for a, b in cuts:
@@ -327,7 +336,10 @@ class B200VideoVAE:
         assert z.shape[0] == 1 and z.shape[1] == 16
         _, _, T, h, w = z.shape
         zin = z[0].to(self.device)
-        size = max(1, self._frames_that_fit(8 * h, 8 * w) // 4)     # latent frames per slice
+        if 4 * T - 3 <= self._frames_that_fit(8 * h, 8 * w):         # the whole clip fits: no slicing state needed
+            size = T
+        else:
+            size = max(1, self._frames_that_fit(8 * h, 8 * w, self.DEC_STATE_BYTES_PER_PIXEL) // 4)   # latent frames
         if self.split_size is not None:
             size = min(size, max(1, self.split_size // 4))
         out = self._run_sliced(self._decode_slice, zin, self._plan(T, size))
@@ -376,7 +388,10 @@ class B200VideoVAE:
         assert x.shape[0] == 1 and x.shape[1] == 3
         _, _, T, H, Wd = x.shape
         xin = x[0].to(self.device)
-        size = max(4, self._frames_that_fit(H, Wd) // 4 * 4)        # sample frames per slice, a multiple of 4
+        if T <= self._frames_that_fit(H, Wd):
+            size = max(4, (T + 3) // 4 * 4)
+        else:                                                        # sample frames per slice, a multiple of 4
+            size = max(4, self._frames_that_fit(H, Wd, self.ENC_STATE_BYTES_PER_PIXEL) // 4 * 4)
         if self.split_size is not None:
             size = min(size, max(4, self.split_size // 4 * 4))
         # slices continue the stride-2 phase of the temporal downsamplers only for clips of 4n+1 frames

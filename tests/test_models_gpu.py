@@ -133,7 +133,7 @@ def test_vae_slices_when_clip_exceeds_memory_model(vae_pair, monkeypatch):
     g = torch.Generator().manual_seed(12)
     z = torch.randn(1, 16, 4, 6, 10, generator=g).cuda()
     full = eng.decode(z).sample
-    monkeypatch.setattr(type(eng), "_frames_that_fit", lambda self, H, W: 4)
+    monkeypatch.setattr(type(eng), "_frames_that_fit", lambda self, H, W, state_bytes_per_pixel=0: 4)
     assert torch.equal(eng.decode(z).sample, full)
 
 
