@@ -46,7 +46,8 @@ struct AttnSmem {
   static constexpr int kP = kQ + ATT_Q_BYTES;
   static constexpr int kK = kP + ATT_P_BYTES;
   static constexpr int kV = kK + ATT_KV_BYTES;
-  static constexpr int kBar = kV + ATT_KV_BYTES;
+  static constexpr int kK1 = kV + ATT_KV_BYTES;      // second K stage
+  static constexpr int kBar = kK1 + ATT_KV_BYTES;
   static constexpr int kTotal = kBar + 128 + 1024;
 };
 
@@ -58,9 +59,10 @@ struct AttnParams {
   float scale_log2;  // softmax_scale * log2(e)
 };
 
-// K and V are single-buffered with separate full/empty barriers: K_{j+1} streams in while tile j is in
-// softmax / P·V, V_{j+1} while tile j+1 is in Q·K^T / softmax; the second CTA on the SM fills the tensor
-// pipe while this one is in its softmax phase.
+// Software pipeline inside a CTA: S_{j+1} = Q K_{j+1}^T is issued as soon as the softmax warps have pulled S_j
+// into registers, so the tensor pipe computes the next scores while tile j is in its softmax, and P_j V_j runs
+// while tile j+1 is in its softmax.  K is double-buffered (loaded two tiles ahead), V single-buffered; the
+// second CTA on the SM (~98 KB smem each) fills the remaining bubbles.
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -82,7 +84,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* s_free = bars + 6;
   uint64_t* p_ready = bars + 7;
   uint64_t* pv_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* k_full1 = bars + 9;                    // second K stage
+  uint64_t* k_empty1 = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -92,6 +96,8 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     mbar_init(q_full, 1);
     mbar_init(k_full, 1);
     mbar_init(k_empty, 1);
+    mbar_init(k_full1, 1);
+    mbar_init(k_empty1, 1);
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
@@ -115,16 +121,26 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       mbar_expect_tx(q_full, ATT_Q_BYTES);
       tma_load_2d(smem + AttnSmem::kQ, &tmap_q, q_full, col0, q_row0);
       tma_load_2d(smem + AttnSmem::kQ + ATT_QH_BYTES, &tmap_q, q_full, col0 + 64, q_row0);
+      auto load_k = [&](int j) {                   // K_j -> stage j & 1 (its previous tenant was K_{j-2})
+        const int st = j & 1;
+        uint64_t* full = st ? k_full1 : k_full;
+        uint64_t* empty = st ? k_empty1 : k_empty;
+        uint8_t* dst = smem + (st ? AttnSmem::kK1 : AttnSmem::kK);
+        const int r0 = s_begin + j * ATT_BN;
+        mbar_wait(empty, ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(full, ATT_KV_BYTES);
+        tma_load_2d(dst, &tmap_k, full, col0, r0);
+        tma_load_2d(dst + ATT_KVH_BYTES, &tmap_k, full, col0 + 64, r0);
+      };
+      load_k(0);
+      if (n_kv > 1) load_k(1);
       for (int j = 0; j < n_kv; ++j) {
         const int r0 = s_begin + j * ATT_BN;
-        mbar_wait(k_empty, (j & 1) ^ 1);
-        mbar_expect_tx(k_full, ATT_KV_BYTES);
-        tma_load_2d(smem + AttnSmem::kK, &tmap_k, k_full, col0, r0);
-        tma_load_2d(smem + AttnSmem::kK + ATT_KVH_BYTES, &tmap_k, k_full, col0 + 64, r0);
         mbar_wait(v_empty, (j & 1) ^ 1);
         mbar_expect_tx(v_full, ATT_KV_BYTES);
         tma_load_2d(smem + AttnSmem::kV, &tmap_v, v_full, col0, r0);
         tma_load_2d(smem + AttnSmem::kV + ATT_KVH_BYTES, &tmap_v, v_full, col0 + 64, r0);
+        if (j + 2 < n_kv) load_k(j + 2);           // waits for Q K_j^T to retire
       }
     }
   } else if (warp == 1) {
@@ -135,19 +151,27 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const uint32_t p_addr = smem_u32(smem + AttnSmem::kP);
       const uint32_t k_addr = smem_u32(smem + AttnSmem::kK);
       const uint32_t v_addr = smem_u32(smem + AttnSmem::kV);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(k_full, j & 1);
-        if (j > 0) mbar_wait(s_free, (j - 1) & 1);     // softmax has finished reading S_{j-1}
+      auto issue_qk = [&](int j) {                 // S_j = Q K_j^T, K_j in stage j & 1
+        const int st = j & 1;
+        mbar_wait(st ? k_full1 : k_full, (j >> 1) & 1);
         tc_fence_after();
+        const uint32_t kb = st ? smem_u32(smem + AttnSmem::kK1) : k_addr;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {                 // contraction over d = 128
           const uint64_t da = umma_desc_kmajor_sw128(q_addr + (kk >> 2) * ATT_QH_BYTES) + uint64_t((kk & 3) * 2);
-          const uint64_t db = umma_desc_kmajor_sw128(k_addr + (kk >> 2) * ATT_KVH_BYTES) + uint64_t((kk & 3) * 2);
+          const uint64_t db = umma_desc_kmajor_sw128(kb + (kk >> 2) * ATT_KVH_BYTES) + uint64_t((kk & 3) * 2);
           umma_bf16(tmem_s, da, db, idesc_qk, kk != 0);
         }
-        umma_commit(k_empty);                            // K_{j+1} may stream in
+        umma_commit(st ? k_empty1 : k_empty);            // this K stage may be refilled (with K_{j+2})
         umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) {
+          mbar_wait(s_free, j & 1);                      // the softmax warps hold S_j in registers
+          issue_qk(j + 1);                               // next scores while tile j is in its softmax
+        }
         mbar_wait(v_full, j & 1);
         mbar_wait(p_ready, j & 1);                       // P_j in smem, O rescaled
         tc_fence_after();
