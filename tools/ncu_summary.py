@@ -20,7 +20,9 @@ lines = ["# ncu --set full captures, round 1 (one launch each; `--clock-control 
 for name, rep in [("conv256_pair (gemm_tcgen05_kernel<256,BF16,pair> 256->256 3x3x3 @2x1080x1920)", "gpurun_out/r1_conv256.ncu-rep"),
                   ("conv128_swap (gemm_tcgen05_kernel<256,BF16,swap> 128->128 3x3x3 @2x2160x3840)", "gpurun_out/r1_conv128.ncu-rep"),
                   ("swiglu_pair (gemm_tcgen05_kernel<256,SWIGLU,pair> 97200x13824x2560)", "gpurun_out/r1_swiglu.ncu-rep"),
-                  ("attn_varlen_kernel (243 windows x 463 tokens x 20 heads)", "gpurun_out/r1_attn.ncu-rep"),
+                  ("attn_varlen_kernel (243 windows x 463 tokens x 20 heads; software-pipelined v3)", "gpurun_out/r1_attn_v3.ncu-rep"),
+                  ("upsample_shuffle (gemm_tcgen05_kernel<256,BF16,pair> + pixel-shuffle store, 256 ch 2x1080x1920 -> 2x2160x3840)", "gpurun_out/r1_upsample_v2.ncu-rep"),
+                  ("conv_shortcut_1x1x1 (gemm_tcgen05_kernel<256,BF16,swap> 256->128 @2x2160x3840)", "gpurun_out/r1_shortcut.ncu-rep"),
                   ("groupnorm_apply_kernel (2x2160x3840x128)", "gpurun_out/prof_gnapply_r1.ncu-rep"),
                   ("groupnorm_stats_kernel (2x2160x3840x128)", "gpurun_out/prof_gnstats_r1.ncu-rep")]:
     if not os.path.exists(rep):
