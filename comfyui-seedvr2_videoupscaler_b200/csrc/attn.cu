@@ -31,7 +31,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 constexpr int ATT_BM = 128;      // q rows per CTA
-constexpr int ATT_BN = 64;       // kv rows per tile (two CTAs are co-resident per SM: ~82 KB smem each)
+constexpr int ATT_BN = 64;       // kv rows per tile (two CTAs are co-resident per SM: ~98 KB smem each)
 constexpr int ATT_D = 128;
 constexpr int ATT_THREADS = 192;
 constexpr int ATT_Q_BYTES = 128 * 128 * 2;          // 32 KB: two [128 x 64] swizzled halves

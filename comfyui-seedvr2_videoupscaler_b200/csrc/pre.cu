@@ -91,21 +91,29 @@ __global__ void __launch_bounds__(256) resize_kernel(const T* __restrict__ in, _
     const int x0 = xfirst[ox], nx = xcount[ox], y0 = yfirst[oy], ny = ycount[oy];
     const float* wx = xw + (long long)ox * K;
     const float* wy = yw + (long long)oy * K;
+    // one pass over the taps for all three channels: each weight is fetched once, the per-channel accumulation
+    // order (horizontal taps left to right, then rows top to bottom) is that of torch's kernel
+    const long long cstride = channels_last ? 1 : (long long)h * w;
+    const long long pstride = channels_last ? cin : 1;
+    const T* base = in + (channels_last ? ((long long)t * h * w) * cin : ((long long)t * 3) * h * w);
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int j = 0; j < ny; ++j) {
+      const T* row = base + ((long long)(y0 + j) * w + x0) * pstride;
+      const float w0 = wx[0];
+      float r[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const long long cstride = channels_last ? 1 : (long long)h * w;
-      const long long pstride = channels_last ? cin : 1;
-      const T* base = in + (channels_last ? ((long long)t * h * w) * cin + c : ((long long)t * 3 + c) * h * w);
-      float acc = 0.f;
-      for (int j = 0; j < ny; ++j) {
-        const T* row = base + ((long long)(y0 + j) * w + x0) * pstride;
-        float r = load_bf16_rounded<T>(row) * wx[0];
-        for (int i = 1; i < nx; ++i) r += load_bf16_rounded<T>(row + i * pstride) * wx[i];
-        acc = (j == 0) ? r * wy[0] : acc + r * wy[j];
+      for (int c = 0; c < 3; ++c) r[c] = load_bf16_rounded<T>(row + c * cstride) * w0;
+      for (int i = 1; i < nx; ++i) {
+        const float wi = wx[i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) r[c] += load_bf16_rounded<T>(row + i * pstride + c * cstride) * wi;
       }
-      (void)cstride;
-      res[c] = rn(acc);
+      const float wj = wy[j];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] = (j == 0) ? r[c] * wj : acc[c] + r[c] * wj;
     }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) res[c] = rn(acc[c]);
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {

@@ -99,7 +99,10 @@ def stream():
 
 
 # kernels launched per C-ABI call (for the bench's gpu_launches count)
-KERNELS_PER_CALL = {"svr2_groupnorm_bf16": 3, "svr2_groupnorm_from_stats_bf16": 2}
+KERNELS_PER_CALL = {"svr2_groupnorm_bf16": 3, "svr2_groupnorm_from_stats_bf16": 2,
+                    "svr2_resize_bicubic_aa_bf16": 3,      # two tap-table kernels + the resize
+                    "svr2_adain_bf16": 2,                  # statistics + apply
+                    "svr2_histogram_match_f32": 2}         # iota + rank scatter (the CUB radix-sort passes are library launches)
 
 
 class Profiler:
