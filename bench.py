@@ -39,6 +39,7 @@ WORKLOADS = {
     "4k_clip64": (64, 2160, 3840, "SeedVR2-3B bf16, 64-frame (->65) 720p->4K as ONE clip on one GPU = BASELINE config 3' "
                                   "(17 latent frames, 2083-token windows, temporally sliced VAE)"),
     "4k_shard_7b": (4, 2160, 3840, "SeedVR2-7B bf16, 4-frame (->5) 720p->4K clip per GPU = BASELINE config 4 shard"),
+    "image_512": (1, 512, 512, "SeedVR2-3B bf16, one 256x256 -> 512x512 image = BASELINE config 1"),
     "720p": (8, 720, 1280, "SeedVR2-3B bf16, 8-frame (->9) 360p->720p clip (smoke)"),
     "tiny": (4, 128, 192, "tiny clip (smoke)"),
 }

@@ -1020,7 +1020,13 @@ extern "C" int svr2_linear_bf16(const void* a, int64_t lda, const void* w, int64
     return set_error(SVR2_ERR_ARG, "svr2_linear_bf16: lda/ldw must be multiples of 8, ldc/N of 8 (4 for fp32 out)");
   if ((epi_flags & EPI_PEXP) && !gate) return set_error(SVR2_ERR_ARG, "EPI_PEXP needs the row log-sum-exp vector (gate)");
   if ((epi_flags & EPI_SWIGLU) && (N % 256)) return set_error(SVR2_ERR_ARG, "SwiGLU needs N % 256 == 0");
-  const int bn = pick_block_n(N, epi_flags);
+  int bn = pick_block_n(N, epi_flags);
+  // Few-row problems (the 58 text tokens of every DiT layer, single images): with 256-column tiles only a handful of
+  // CTAs would walk the whole K loop.  Narrower tiles spread the same work over up to half the SMs.
+  if (!(epi_flags & (EPI_SWIGLU | EPI_ROWSTAT | EPI_PEXP))) {
+    const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    while (bn > 32 && 2 * m_tiles * ((N + bn - 1) / bn) <= num_sms()) bn /= 2;
+  }
   CUtensorMap ta, tb;
   uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)lda * 2};
   uint32_t ba[2] = {BLOCK_K, BLOCK_M};
