@@ -237,6 +237,22 @@ __global__ void __launch_bounds__(256) blend_overlap_kernel(const uint4* __restr
   }
 }
 
+// fp32 frames (multi-GPU merge, inference_cli.py:1241-1270): prev * w_prev + cur * w_cur with torch's three
+// separately rounded ops (no FMA contraction)
+__global__ void __launch_bounds__(256) blend_overlap_f32_kernel(const float4* __restrict__ prev,
+                                                                const float4* __restrict__ cur, float4* __restrict__ out,
+                                                                const float* __restrict__ w_prev,
+                                                                const float* __restrict__ w_cur, long long vec_per_frame) {
+  const int f = blockIdx.y;
+  const float wp = w_prev[f], wc = w_cur[f];
+  const long long base = (long long)f * vec_per_frame;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < vec_per_frame; i += (long long)gridDim.x * 256) {
+    const float4 a = prev[base + i], b = cur[base + i];
+    out[base + i] = make_float4(__fadd_rn(__fmul_rn(a.x, wp), __fmul_rn(b.x, wc)), __fadd_rn(__fmul_rn(a.y, wp), __fmul_rn(b.y, wc)),
+                                __fadd_rn(__fmul_rn(a.z, wp), __fmul_rn(b.z, wc)), __fadd_rn(__fmul_rn(a.w, wp), __fmul_rn(b.w, wc)));
+  }
+}
+
 inline int grid_for(long long n, int per_block = 256, int waves = 16) {
   long long b = (n + per_block - 1) / per_block;
   const long long cap = (long long)num_sms() * waves;
@@ -360,4 +376,17 @@ extern "C" int svr2_blend_overlap_bf16(const void* prev_tail, const void* cur_he
   blend_overlap_kernel<<<dim3(bx, overlap), 256, 0, (cudaStream_t)stream>>>((const uint4*)prev_tail, (const uint4*)cur_head,
                                                                              (uint4*)out, w_prev, w_cur, vec);
   return check_launch("blend_overlap");
+}
+
+extern "C" int svr2_blend_overlap_f32(const float* prev_tail, const float* cur_head, float* out, const float* w_prev,
+                                      const float* w_cur, int overlap, int64_t frame_elems, void* stream) {
+  if (overlap <= 0 || frame_elems <= 0) return set_error(SVR2_ERR_ARG, "svr2_blend_overlap_f32: empty input");
+  if (frame_elems % 4) return set_error(SVR2_ERR_ARG, "svr2_blend_overlap_f32: frame_elems must be a multiple of 4");
+  if (overlap > 65535) return set_error(SVR2_ERR_ARG, "svr2_blend_overlap_f32: overlap <= 65535");
+  const long long vec = frame_elems / 4;
+  int bx = grid_for(vec, 256, 8) / overlap;
+  if (bx < 1) bx = 1;
+  blend_overlap_f32_kernel<<<dim3(bx, overlap), 256, 0, (cudaStream_t)stream>>>((const float4*)prev_tail, (const float4*)cur_head,
+                                                                                 (float4*)out, w_prev, w_cur, vec);
+  return check_launch("blend_overlap_f32");
 }

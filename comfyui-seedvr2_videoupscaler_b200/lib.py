@@ -56,6 +56,7 @@ SIGNATURES = {
     "svr2_histogram_match_f32": [_P, _P, _P, c_int64, _P, c_int64, _P],
     "svr2_sample_to_image_bf16": [_P, _P, c_int, c_int64, _P],
     "svr2_blend_overlap_bf16": [_P, _P, _P, _P, _P, c_int, c_int64, _P],
+    "svr2_blend_overlap_f32": [_P, _P, _P, _P, _P, c_int, c_int64, _P],
     "svr2_resize_scratch_bytes": [c_int, c_int, c_int, c_int],
     "svr2_resize_bicubic_aa_bf16": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int64,
                                     _P],

@@ -61,17 +61,38 @@ def blend_weights(overlap: int, dtype=torch.bfloat16):
 
 def blend_overlap(prev_tail: torch.Tensor, cur_head: torch.Tensor) -> torch.Tensor:
     """Cross-fade of the ``overlap`` frames two neighbouring ranges share (``blend_overlapping_frames``,
-    generation_utils.py:284-312): [overlap, H, W, C] bf16 each, on the GPU (one libsvr2 kernel)."""
+    generation_utils.py:284-312): [overlap, H, W, C] each, bf16 (inside the pipeline) or fp32 (the multi-GPU merge),
+    on the GPU (one libsvr2 kernel); weights and rounding points follow the frames' dtype."""
     from . import lib
     assert prev_tail.shape == cur_head.shape and prev_tail.is_cuda
     n = prev_tail.shape[0]
-    a, b = prev_tail.to(torch.bfloat16).contiguous(), cur_head.to(torch.bfloat16).contiguous()
-    w_prev, w_cur = blend_weights(n, torch.bfloat16)
+    dt = torch.float32 if prev_tail.dtype == torch.float32 else torch.bfloat16
+    a, b = prev_tail.to(dt).contiguous(), cur_head.to(dt).contiguous()
+    w_prev, w_cur = blend_weights(n, dt)
     wp, wc = w_prev.float().to(a.device), w_cur.float().to(a.device)
     elems = a[0].numel()
     if elems % 8:
         raise ValueError("frames must hold a multiple of 8 values")
     out = torch.empty_like(a)
-    lib.call("svr2_blend_overlap_bf16", lib.ptr(a), lib.ptr(b), lib.ptr(out), lib.ptr(wp), lib.ptr(wc), n, elems,
-             lib.stream(), nbytes=6.0 * a.numel())
+    name = "svr2_blend_overlap_f32" if dt == torch.float32 else "svr2_blend_overlap_bf16"
+    lib.call(name, lib.ptr(a), lib.ptr(b), lib.ptr(out), lib.ptr(wp), lib.ptr(wc), n, elems, lib.stream(),
+             nbytes=3.0 * a.numel() * a.element_size())
     return out
+
+
+def merge_shards(chunks: List[torch.Tensor], overlap: int, blend=None) -> torch.Tensor:
+    """Concatenate the per-rank results in rank order, cross-fading the ``overlap`` frames a chunk shares with the
+    accumulated result (inference_cli.py:1241-1274; fp32 like the reference).  ``blend(prev_tail, cur_head)``
+    defaults to the libsvr2 kernel."""
+    blend = blend or blend_overlap
+    chunks = [c.float() for c in chunks]
+    if overlap <= 0 or len(chunks) == 1:
+        return torch.cat(chunks, 0)
+    result = chunks[0]
+    for c in chunks[1:]:
+        if c.shape[0] > overlap and result.shape[0] >= overlap:
+            blended = blend(result[-overlap:], c[:overlap])
+            result = torch.cat([result[:-overlap], blended, c[overlap:]], 0)
+        elif c.shape[0] > overlap:       # chunk too small to blend into: append its non-overlapping part
+            result = torch.cat([result, c[overlap:]], 0)
+    return result

@@ -178,6 +178,11 @@ int svr2_sample_to_image_bf16(const void* sample, void* image, int frames, int64
 int svr2_blend_overlap_bf16(const void* prev_tail, const void* cur_head, void* out, const float* w_prev,
                             const float* w_cur, int overlap, int64_t frame_elems, void* stream);
 
+/* The same cross-fade on fp32 frames — the merge of per-GPU results (inference_cli.py:1241-1270): out = prev * w_prev +
+ * cur * w_cur with three separately rounded fp32 operations. */
+int svr2_blend_overlap_f32(const float* prev_tail, const float* cur_head, float* out, const float* w_prev,
+                           const float* w_cur, int overlap, int64_t frame_elems, void* stream);
+
 /* ---- Clip pre-processing (prepare_video_transforms, src/core/generation_utils.py:72-84).
  * Antialiased bicubic resize (torchvision resize -> torch _upsample_bicubic2d_aa semantics, fp32 accumulation, result
  * rounded to bf16) of frames given as [T,h,w,cin] (channels_last != 0, first 3 channels) or [T,3,h,w]; in_dtype

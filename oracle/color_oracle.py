@@ -167,9 +167,10 @@ def sample_to_image(sample: torch.Tensor, mode: str = "ref_bf16") -> torch.Tenso
 
 
 def blend_overlapping_frames(prev_tail: torch.Tensor, cur_head: torch.Tensor, overlap: int) -> torch.Tensor:
-    """generation_utils.py:284-312 on bf16 frames [overlap, H, W, C]: Hann cross-fade over the middle third for
-    overlap >= 3, linear below; weights and products carry the frames' dtype (every op rounds to bf16)."""
-    dt = torch.bfloat16
+    """generation_utils.py:284-312 on frames [overlap, H, W, C]: Hann cross-fade over the middle third for
+    overlap >= 3, linear below; weights and products carry the frames' dtype (bf16 inside the pipeline: every op
+    rounds to bf16; fp32 in the multi-GPU merge of inference_cli.py:1241-1270).  Returns fp32 values."""
+    dt = prev_tail.dtype
     if overlap >= 3:
         t = torch.linspace(0.0, 1.0, steps=overlap, dtype=dt)
         u = ((t - 1.0 / 3.0) / (2.0 / 3.0 - 1.0 / 3.0)).clamp(0.0, 1.0)
@@ -178,5 +179,20 @@ def blend_overlapping_frames(prev_tail: torch.Tensor, cur_head: torch.Tensor, ov
         w_prev = torch.linspace(1.0, 0.0, steps=overlap, dtype=dt)
     w_prev = w_prev.view(overlap, 1, 1, 1)
     w_cur = 1.0 - w_prev
-    a, b = prev_tail.to(dt), cur_head.to(dt)
-    return (a * w_prev + b * w_cur).float()
+    return (prev_tail * w_prev + cur_head.to(dt) * w_cur).float()
+
+
+def merge_shards(chunks, overlap: int) -> torch.Tensor:
+    """inference_cli.py:1241-1274: concatenate per-GPU results (fp32), cross-fading the `overlap` frames that a
+    chunk shares with the accumulated result; chunks not longer than the overlap contribute nothing."""
+    chunks = [c.float() for c in chunks]
+    if overlap <= 0 or len(chunks) == 1:
+        return torch.cat(chunks, 0)
+    result = chunks[0]
+    for c in chunks[1:]:
+        if c.shape[0] > overlap and result.shape[0] >= overlap:
+            blended = blend_overlapping_frames(result[-overlap:], c[:overlap], overlap)
+            result = torch.cat([result[:-overlap], blended, c[overlap:]], 0)
+        elif c.shape[0] > overlap:
+            result = torch.cat([result, c[overlap:]], 0)
+    return result

@@ -206,7 +206,12 @@ def run_color_cases():
         assert ref_out.dtype == torch.bfloat16
         assert torch.equal(ref_out.float(), co.blend_overlapping_frames(a, b, ov)), ov
         blends[f"ov{ov}"] = ref_out.float().numpy().astype(np.float32)
-    print("blend_overlapping_frames: oracle == reference (bit-exact) for overlaps 1,2,3,4,7,8")
+    for ov in (2, 5):       # fp32 frames: the multi-GPU merge of inference_cli.py:1241-1270
+        a, b = torch.rand(ov, 6, 8, 3, generator=g), torch.rand(ov, 6, 8, 3, generator=g)
+        ref_out = ns["blend_overlapping_frames"](a, b, ov)
+        assert ref_out.dtype == torch.float32 and torch.equal(ref_out, co.blend_overlapping_frames(a, b, ov)), ov
+        blends[f"f32_ov{ov}"] = ref_out.numpy()
+    print("blend_overlapping_frames: oracle == reference (bit-exact) for overlaps 1,2,3,4,7,8 (bf16) and 2,5 (fp32)")
     np.savez_compressed(os.path.join(GOLD, "blend_overlap.npz"), **blends)
 
 

@@ -127,3 +127,22 @@ def test_blend_overlap_oracle_matches_reference_golden(pkg):
         w_prev, w_cur = shard.blend_weights(ov)
         ref = (a * w_prev.view(ov, 1, 1, 1) + b * w_cur.view(ov, 1, 1, 1)).float()
         assert torch.equal(ref, out)
+    for ov in (2, 5):       # fp32 frames (multi-GPU merge)
+        a, b = torch.rand(ov, 6, 8, 3, generator=g), torch.rand(ov, 6, 8, 3, generator=g)
+        assert torch.equal(color_oracle.blend_overlapping_frames(a, b, ov), torch.from_numpy(gold[f"f32_ov{ov}"]))
+
+
+def test_merge_shards_host_logic(pkg):
+    """shard.merge_shards (inference_cli.py:1241-1274) with the oracle blend plugged in == the oracle's merge, incl. the
+    'chunk not longer than the overlap' edge cases; partition + merge restores the frame count."""
+    import importlib
+    shard = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.shard")
+    g = torch.Generator().manual_seed(5)
+    blend = lambda p, c: color_oracle.blend_overlapping_frames(p, c, p.shape[0])
+    for total, world, ov in ((23, 3, 2), (16, 2, 4), (9, 4, 3), (5, 4, 2), (12, 2, 0)):
+        parts = shard.partition_frames(total, world, ov)
+        chunks = [torch.rand(b - a, 4, 6, 3, generator=g) for a, b in parts]
+        out = shard.merge_shards(chunks, ov, blend=blend)
+        assert torch.equal(out, color_oracle.merge_shards(chunks, ov))
+        if all(c.shape[0] > ov for c in chunks):
+            assert out.shape[0] == total

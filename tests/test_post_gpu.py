@@ -190,3 +190,22 @@ def test_blend_overlap_vs_reference_golden(pkg):
     a = torch.rand(3, 270, 480, 3, generator=g).to(torch.bfloat16)
     b = torch.rand(3, 270, 480, 3, generator=g).to(torch.bfloat16)
     assert torch.equal(shard.blend_overlap(a.cuda(), b.cuda()).float().cpu(), color_oracle.blend_overlapping_frames(a, b, 3))
+
+
+def test_merge_shards_fp32_kernel(pkg):
+    """Per-rank results merged with the fp32 cross-fade kernel == the oracle's merge (== inference_cli.py:1241-1274),
+    bit for bit; the fp32 blend also matches the reference goldens."""
+    shard = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.shard")
+    gold = np.load(os.path.join(GOLD, "blend_overlap.npz"))
+    g = torch.Generator().manual_seed(21)
+    for ov in (1, 2, 3, 4, 7, 8):                      # replay the generator of oracle/make_golden.py
+        torch.rand(ov, 6, 8, 3, generator=g); torch.rand(ov, 6, 8, 3, generator=g)
+    for ov in (2, 5):
+        a, b = torch.rand(ov, 6, 8, 3, generator=g), torch.rand(ov, 6, 8, 3, generator=g)
+        assert torch.equal(shard.blend_overlap(a.cuda(), b.cuda()).cpu(), torch.from_numpy(gold[f"f32_ov{ov}"]))
+    g = torch.Generator().manual_seed(6)
+    for total, world, ov in ((23, 3, 2), (16, 2, 4), (9, 4, 3)):
+        parts = shard.partition_frames(total, world, ov)
+        chunks = [torch.rand(b - a, 16, 24, 3, generator=g).to(torch.bfloat16) for a, b in parts]
+        out = shard.merge_shards([c.cuda() for c in chunks], ov)
+        assert out.dtype == torch.float32 and torch.equal(out.cpu(), color_oracle.merge_shards(chunks, ov))
