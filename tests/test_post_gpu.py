@@ -65,6 +65,15 @@ def test_color_fix_medium_size_vs_oracle(cf):
     assert psnr(l1, color_oracle.lab_color_transfer(content, style, luminance_weight=1.0)) > 55.0
 
 
+def test_color_fix_odd_sizes_vs_oracle(cf):
+    """Odd width / height (the two-pixels-per-thread wavelet kernel's ragged last column, capped dilations)."""
+    content, style = color_inputs(2, 37, 53, seed=13)
+    c, s = content.cuda(), style.cuda()
+    assert frac_equal(cf.wavelet_reconstruction(c, s), color_oracle.wavelet_reconstruction(content, style)) > 0.999
+    assert psnr(cf.adaptive_instance_normalization(c, s), color_oracle.adaptive_instance_normalization(content, style)) > 60.0
+    assert psnr(cf.lab_color_transfer(c, s, None), color_oracle.lab_color_transfer(content, style)) > 55.0
+
+
 def test_histogram_match_is_exact_rank_mapping(svr2lib):
     """Size-independent properties at 4M elements: the output is a permutation of the reference values and
     preserves the order of the source."""
