@@ -1,4 +1,4 @@
-"""scratch: run on GPU, print PSNRs of the engine vs goldens / oracle."""
+"""Run on the GPU box: print the PSNRs of the engines vs the reference goldens and the oracle (what the parity tests assert)."""
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tools/)
