@@ -423,6 +423,92 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
   }
 }
 
+// Same arithmetic, leaner: the bf16 rounding of the normalised value is one cvt.rn.bf16x2 per channel pair (instead
+// of an integer round-to-nearest-even per value), six 16-byte loads in flight per thread and at most 64 registers
+// so that four blocks fit an SM — the kernel is latency-bound at the power-capped clock, not DRAM-bound.
+__global__ void __launch_bounds__(256, 4) groupnorm_apply_v2_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                    __nv_bfloat16* __restrict__ y, int hw, int C,
+                                                                    int silu, int out_t_pad, int out_dup_head,
+                                                                    const float2* __restrict__ coef) {
+  const int f = blockIdx.y;
+  const int cvec = C / 8;
+  const long long nvec = (long long)hw * cvec;
+  const uint4* __restrict__ xf = reinterpret_cast<const uint4*>(x + (long long)f * hw * C);
+  uint4* __restrict__ yf = reinterpret_cast<uint4*>(y + (long long)(f + out_t_pad) * hw * C);
+  const long long halo = nvec;                       // vectors per frame
+  const int cv = threadIdx.x % cvec;                 // every stride below is a multiple of 256: fixed channel octet
+  float ca[8], cb[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float2 t = coef[(long long)f * C + cv * 8 + e];
+    ca[e] = t.x;
+    cb[e] = t.y;
+  }
+  const bool dup = out_dup_head && f == 0;
+  auto apply = [&](const uint4& r) -> uint4 {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float t0 = fmaf(__uint_as_float(w[e] << 16), ca[2 * e], cb[2 * e]);
+      const float t1 = fmaf(__uint_as_float(w[e] & 0xffff0000u), ca[2 * e + 1], cb[2 * e + 1]);
+      uint32_t pk = pack_bf16x2(t0, t1);              // F.group_norm output is bf16
+      if (silu) pk = pack_bf16x2(silu_fast(__uint_as_float(pk << 16)), silu_fast(__uint_as_float(pk & 0xffff0000u)));
+      o[e] = pk;
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  const long long stride = (long long)gridDim.x * 256;
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  for (; i + 5 * stride < nvec; i += 6 * stride) {
+    uint4 r[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) r[u] = __ldcs(xf + i + u * stride);        // streamed once
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const uint4 pk = apply(r[u]);
+      yf[i + u * stride] = pk;
+      if (dup) {
+        yf[i + u * stride - halo] = pk;
+        yf[i + u * stride - 2 * halo] = pk;
+      }
+    }
+  }
+  for (; i < nvec; i += stride) {
+    const uint4 pk = apply(xf[i]);
+    yf[i] = pk;
+    if (dup) {
+      yf[i - halo] = pk;
+      yf[i - 2 * halo] = pk;
+    }
+  }
+}
+
+// SVR2_GN_APPLY=v1 selects the first version (A/B measurements)
+static bool gn_apply_v2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SVR2_GN_APPLY");
+    v = (e && e[0] == 'v' && e[1] == '1') ? 0 : 1;
+  }
+  return v != 0;
+}
+static void launch_gn_apply(const void* x, void* y, int frames, int hw, int C, int silu, int out_t_pad, int out_dup_head,
+                            const float2* coef, cudaStream_t s) {
+  const long long nvec = (long long)hw * C / 8;
+  if (gn_apply_v2()) {
+    int bx = (int)((nvec + 256 * 12 - 1) / (256 * 12));
+    if (bx < 1) bx = 1;
+    groupnorm_apply_v2_kernel<<<dim3(bx, frames), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, C, silu,
+                                                               out_t_pad, out_dup_head, coef);
+  } else {
+    int bx = (int)((nvec + 256 * 8 - 1) / (256 * 8));
+    if (bx < 1) bx = 1;
+    groupnorm_apply_kernel<<<dim3(bx, frames), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, C, silu,
+                                                            out_t_pad, out_dup_head, coef);
+  }
+}
+
 // ------------------------------------------------------------------ softmax rows fp32 -> bf16
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, long long lds,
                                                            __nv_bfloat16* __restrict__ p, long long ldp, int cols) {
@@ -711,11 +797,7 @@ extern "C" int svr2_groupnorm_bf16(const void* x, void* y, int frames, int hw, i
                                                    (const __nv_bfloat16*)beta, eps, coef);
   rc = check_launch("groupnorm_finalize");
   if (rc) return rc;
-  const long long nvec = (long long)hw * C / 8;
-  int bx = (int)((nvec + 256 * 8 - 1) / (256 * 8));
-  if (bx < 1) bx = 1;
-  groupnorm_apply_kernel<<<dim3(bx, frames), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, C, silu,
-                                                          out_t_pad, out_dup_head, coef);
+  launch_gn_apply(x, y, frames, hw, C, silu, out_t_pad, out_dup_head, coef, s);
   return check_launch("groupnorm_apply");
 }
 
@@ -734,11 +816,7 @@ extern "C" int svr2_groupnorm_from_stats_bf16(const void* x, void* y, int frames
                                                          coef);
   int rc = check_launch("groupnorm_finalize_fused");
   if (rc) return rc;
-  const long long nvec = (long long)hw * C / 8;
-  int bx = (int)((nvec + 256 * 8 - 1) / (256 * 8));
-  if (bx < 1) bx = 1;
-  groupnorm_apply_kernel<<<dim3(bx, frames), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, C, silu,
-                                                          out_t_pad, out_dup_head, coef);
+  launch_gn_apply(x, y, frames, hw, C, silu, out_t_pad, out_dup_head, coef, s);
   return check_launch("groupnorm_apply");
 }
 
