@@ -283,13 +283,13 @@ def main():
     fm = flop_model(frames_pad, H, W, variant)
     # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of one representative
     # launch (profiles/ncu_full_r1.json, conv 256->256 3x3x3 at 2x1080x1920 on the CTA-pair kernel)
-    traffic = None
+    traffic, traffic_detail = None, None
     try:
         cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_full_r1.json")))["conv256_pair"]
-        traffic = {"bytes_per_launch": (float(cap["dram__bytes_read.sum"]) + float(cap["dram__bytes_write.sum"])) * 1e9,
-                   "algorithmic_bytes_per_launch": (4 + 2) * 1080 * 1920 * 256 * 2.0,
-                   "launch": "conv3d 256->256 3x3x3, 2 frames 1080x1920 (+2 halo frames), ncu --set full",
-                   "tensor_pipe_active_pct": float(cap["sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"])}
+        traffic = (float(cap["dram__bytes_read.sum"]) + float(cap["dram__bytes_write.sum"])) * 1e9   # bytes per launch
+        traffic_detail = {"algorithmic_bytes_per_launch": (4 + 2) * 1080 * 1920 * 256 * 2.0,
+                          "launch": "conv3d 256->256 3x3x3, 2 frames 1080x1920 (+2 halo frames), ncu --set full",
+                          "tensor_pipe_active_pct": float(cap["sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"])}
     except Exception:
         pass
     if args.phases:
@@ -319,7 +319,7 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (Linear + implicit-GEMM Conv3d + upsample)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": traffic, "launches": g_calls, "kernel_ms_per_step": g_ms / args.steps,
+                     "traffic": traffic, "traffic_detail": traffic_detail, "launches": g_calls, "kernel_ms_per_step": g_ms / args.steps,
                      "share_of_step": g_ms / ms, "peak_source": peak_src},
         "clocks": sampler.result(),
     }
