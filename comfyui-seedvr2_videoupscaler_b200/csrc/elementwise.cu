@@ -175,6 +175,82 @@ __global__ void __launch_bounds__(256) qk_norm_rope_window_kernel(
   }
 }
 
+// v2 of the kernel above (SVR2_QK_ROPE=v2): same arithmetic, q/k/v of up to three heads per warp fetched up front
+// one block per output row (window-ordered); warp w handles heads w, w+nwarps, ...; lane = 4 dims.
+__global__ void __launch_bounds__(256) qk_norm_rope_window_v2_kernel(
+    const __nv_bfloat16* __restrict__ qkv_vid, const __nv_bfloat16* __restrict__ qkv_txt,
+    const int32_t* __restrict__ row_src, const int32_t* __restrict__ row_rope, const float* __restrict__ cos_tab,
+    const float* __restrict__ sin_tab, int nfreq, const float* __restrict__ wq_vid, const float* __restrict__ wk_vid,
+    const float* __restrict__ wq_txt, const float* __restrict__ wk_txt, float eps, int heads,
+    __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, __nv_bfloat16* __restrict__ v) {
+  const long long r = blockIdx.x;
+  const int src = row_src[r];
+  const bool is_txt = src < 0;
+  const int inner = heads * 128;
+  const __nv_bfloat16* base = is_txt ? qkv_txt + (long long)(-src - 1) * 3 * inner : qkv_vid + (long long)src * 3 * inner;
+  const float* wq = is_txt ? wq_txt : wq_vid;
+  const float* wk = is_txt ? wk_txt : wk_vid;
+  const int ri[3] = {row_rope[r * 3 + 0], row_rope[r * 3 + 1], row_rope[r * 3 + 2]};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int d0 = lane * 4;
+  const int rot = 6 * nfreq;  // rotated dims
+  // per-lane cos/sin for the two pairs (d0,d0+1), (d0+2,d0+3)
+  float cs[2], sn[2];
+#pragma unroll
+  for (int pi = 0; pi < 2; ++pi) {
+    const int d = d0 + 2 * pi;
+    cs[pi] = 1.f;
+    sn[pi] = 0.f;
+    if (d < rot) {
+      const int axis = d / (2 * nfreq), j = (d % (2 * nfreq)) >> 1;
+      const int tr = ri[axis];
+      if (tr >= 0) {
+        cs[pi] = cos_tab[tr * nfreq + j];
+        sn[pi] = sin_tab[tr * nfreq + j];
+      }
+    }
+  }
+  const float4 wq4 = *reinterpret_cast<const float4*>(wq + d0);
+  const float4 wk4 = *reinterpret_cast<const float4*>(wk + d0);
+  // The kernel is latency-bound (one 256-byte row segment per warp and load): fetch q, k and v of up to three heads
+  // per warp before touching any of them, so ~2.3 KB per warp are in flight instead of 256 B.
+  constexpr int kHeadsPerPass = 3;
+  for (int h0 = warp; h0 < heads; h0 += nwarps * kHeadsPerPass) {
+    uint2 raw[kHeadsPerPass][3];
+#pragma unroll
+    for (int i = 0; i < kHeadsPerPass; ++i) {
+      const int h = h0 + i * nwarps;
+      if (h < heads) {
+#pragma unroll
+        for (int which = 0; which < 3; ++which)
+          raw[i][which] = *reinterpret_cast<const uint2*>(base + which * inner + h * 128 + d0);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kHeadsPerPass; ++i) {
+      const int h = h0 + i * nwarps;
+      if (h >= heads) break;
+      const long long o_off = (r * heads + h) * 128 + d0;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw[i][which]);
+        float2 a = __bfloat1622float2(hh[0]), b = __bfloat1622float2(hh[1]);
+        float ss = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+        ss = warp_sum(ss);
+        const float rr = 1.0f / sqrtf(ss * (1.0f / 128.0f) + eps);
+        const float4 w4 = which == 0 ? wq4 : wk4;
+        float x0 = a.x * rr * w4.x, x1 = a.y * rr * w4.y, x2 = b.x * rr * w4.z, x3 = b.y * rr * w4.w;
+        // interleaved-pair rotation: (x0,x1) -> (x0 c - x1 s, x1 c + x0 s)
+        const float y0 = x0 * cs[0] - x1 * sn[0], y1 = x1 * cs[0] + x0 * sn[0];
+        const float y2 = x2 * cs[1] - x3 * sn[1], y3 = x3 * cs[1] + x2 * sn[1];
+        uint2 outv = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+        *reinterpret_cast<uint2*>((which == 0 ? q : k) + o_off) = outv;
+      }
+      *reinterpret_cast<uint2*>(v + o_off) = raw[i][2];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ text mean over windows
 __global__ void txt_window_mean_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                        int n_win, int l, int dim) {
@@ -746,7 +822,13 @@ extern "C" int svr2_qk_norm_rope_window_bf16(const void* qkv_vid, const void* qk
   if (total <= 0) return SVR2_OK;
   if (6 * nfreq > 128) return set_error(SVR2_ERR_ARG, "rope: 6*nfreq > head_dim");
   const int threads = heads >= 8 ? 256 : 32 * heads;   // 8 warps loop over the heads (one warp per head was slower: 54 vs 34 ms)
-  qk_norm_rope_window_kernel<<<total, threads, 0, (cudaStream_t)stream>>>(
+  static int v2 = -1;
+  if (v2 < 0) {
+    const char* e = getenv("SVR2_QK_ROPE");
+    v2 = (e && e[0] == 'v' && e[1] == '2') ? 1 : 0;     // v2 is opt-in until it has been measured in the pipeline
+  }
+  auto kern = v2 ? qk_norm_rope_window_v2_kernel : qk_norm_rope_window_kernel;
+  kern<<<total, threads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)qkv_vid, (const __nv_bfloat16*)qkv_txt, row_src, row_rope, cos_tab, sin_tab, nfreq, wq_vid,
       wk_vid, wq_txt, wk_txt, eps, heads, (__nv_bfloat16*)q, (__nv_bfloat16*)k, (__nv_bfloat16*)v);
   return check_launch("qk_norm_rope_window");
