@@ -130,12 +130,17 @@ class GraphedClip:
                                                     clip_kwargs.get("max_resolution", 0)),
                                 generator=g, device=dev, dtype=torch.bfloat16)
         self.noise = noise.to(dev, torch.bfloat16).clone()
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):           # shape-dependent tables, kernel attributes, allocator warm-up
-            for _ in range(max(1, warmup)):
-                engine.upscale_clip(self.static_in, noise=self.noise, **clip_kwargs)
-        torch.cuda.current_stream(dev).wait_stream(side)
+        if warmup > 0:                          # shape-dependent tables and kernel attributes (skip with warmup=0
+            side = torch.cuda.Stream(device=dev)    # when the engine has already run this clip shape eagerly)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    engine.upscale_clip(self.static_in, noise=self.noise, **clip_kwargs)
+            torch.cuda.current_stream(dev).wait_stream(side)
+        # the graph's private pool holds one whole clip of intermediates (~100 GB at 4K): hand the eager path's cached
+        # blocks back first so both never have to coexist
+        torch.cuda.synchronize(dev)
+        torch.cuda.empty_cache()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = engine.upscale_clip(self.static_in, noise=self.noise, **clip_kwargs)
