@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_double, c_float, c_int, c_int32, c_int64, c_void_p, POINTER
+from ctypes import c_float, c_int, c_int64, c_void_p, POINTER
 
 import torch
 

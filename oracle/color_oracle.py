@@ -22,7 +22,6 @@ same math without intermediate rounding.  LAB runs in fp32 in the reference
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 _K1 = (0.25, 0.5, 0.25)   # the 3x3 kernel of color_fix.py:142-146 is the outer product of (1,2,1)/4
 

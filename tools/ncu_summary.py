@@ -1,5 +1,5 @@
 """Turns gpurun_out/*.ncu-rep + the launch list into the tracked summaries under profiles/ (run in the build container)."""
-import csv, io, subprocess, sys, collections, json, os
+import csv, io, subprocess, collections, json, os
 OUT = "profiles"
 os.makedirs(OUT, exist_ok=True)
 KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",

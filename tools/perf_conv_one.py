@@ -27,7 +27,6 @@ elif which == "attn":       # DiT window attention at the 4K shard: 243 windows 
     o = torch.empty_like(q)
     fn = lambda: lib.attn_varlen(q, k, v, cu, 463, out=o)
 elif which == "upsample":   # Upsample3D 1x1x1 conv + pixel shuffle, 256 ch at 2 x 1080 x 1920 -> 2 x 2160 x 3840
-    from ctypes import c_void_p
     T, H, W, C = 2, 1080, 1920, 256
     x = rnd(T, H, W, C); w = rnd(4 * C, C) * 0.05; b = rnd(4 * C)
     y = torch.empty(T + 2, 2 * H, 2 * W, C, device=dev, dtype=torch.bfloat16)

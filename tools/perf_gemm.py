@@ -1,6 +1,6 @@
 """Micro-benchmark of the tcgen05 GEMM / implicit-conv kernel on representative shapes
 (used for ncu captures and kernel tuning; not a pytest)."""
-import os, sys, time, importlib
+import os, sys, importlib
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tools/)
 sys.path.insert(0, ROOT)
