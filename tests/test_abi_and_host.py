@@ -142,3 +142,23 @@ def test_checkpoint_loader_formats(pkg, tmp_path):
     full = {"vid_in.proj.weight": torch.empty(2560, 132)}
     assert pkg.weights.detect_dit_variant(full) == "3b"
     assert pkg.weights.detect_dit_variant({"vid_in.proj.weight": torch.empty(3072, 132)}) == "7b"
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm) runs without a GPU and prints ONE JSON line with the
+    keys of the bench contract, the same metric / unit / direction as the B200 arm and `impl: reference`."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "upscaled frames/sec SeedVR2-3B 720p->4K" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
