@@ -195,3 +195,100 @@ def merge_shards(chunks, overlap: int) -> torch.Tensor:
         elif c.shape[0] > overlap:
             result = torch.cat([result, c[overlap:]], 0)
     return result
+
+
+# ---------------------------------------------------------------- HSV / wavelet-adaptive (round-2 groundwork)
+# The B200 engine does not ship these two modes yet (color_fix.apply_color_correction raises for them); the
+# restatements below are pinned to the reference so that the kernels can be built against them next.
+def rgb_to_hsv(rgb01: torch.Tensor) -> torch.Tensor:
+    """color_fix.py:614-649.  rgb [B,3,H,W] in [0,1] -> (h, s, v) in [0,1]; on channel ties the later of the
+    reference's three masked assignments wins (blue over green over red)."""
+    r, g, b = rgb01[:, 0], rgb01[:, 1], rgb01[:, 2]
+    maxc, minc = rgb01.max(1).values, rgb01.min(1).values
+    rng = maxc - minc
+    ok = rng > 1e-10
+    rnz = torch.where(ok, rng, torch.ones_like(rng))
+    h = torch.zeros_like(maxc)
+    h = torch.where((maxc == r) & ok, torch.remainder((g - b) / rnz, 6.0), h)
+    h = torch.where((maxc == g) & ok, (b - r) / rnz + 2.0, h)
+    h = torch.where((maxc == b) & ok, (r - g) / rnz + 4.0, h)
+    h = h / 6.0
+    s = torch.where(maxc > 1e-10, rng / maxc.clamp(min=1e-10), torch.zeros_like(maxc))
+    return torch.stack([h, s, maxc], 1)
+
+
+def hsv_to_rgb(hsv: torch.Tensor) -> torch.Tensor:
+    """color_fix.py:652-695."""
+    h, s, v = hsv[:, 0] * 6.0, hsv[:, 1], hsv[:, 2]
+    i = torch.floor(h).long() % 6
+    f = h - torch.floor(h)
+    p, q, t = v * (1.0 - s), v * (1.0 - s * f), v * (1.0 - s * (1.0 - f))
+    table = ((v, t, p), (q, v, p), (p, v, t), (p, q, v), (t, p, v), (v, p, q))
+    out = [torch.zeros_like(v) for _ in range(3)]
+    for k, sel in enumerate(table):
+        m = i == k
+        for c in range(3):
+            out[c] = torch.where(m, sel[c], out[c])
+    return torch.stack(out, 1)
+
+
+def histogram_match_1d(source: torch.Tensor, reference: torch.Tensor) -> torch.Tensor:
+    """color_fix.py:744-769: rank mapping with the quantile index (linspace * (n_ref - 1)).long() when the two
+    populations differ in size."""
+    order = torch.sort(source, stable=True).indices
+    ref_sorted = torch.sort(reference).values
+    n_s, n_r = source.numel(), reference.numel()
+    if n_s != n_r:
+        idx = (torch.linspace(0, 1, n_s) * (n_r - 1)).long().clamp_(0, n_r - 1)
+        ref_sorted = ref_sorted[idx]
+    out = torch.empty_like(source)
+    out[order] = ref_sorted
+    return out
+
+
+def hue_conditional_saturation_match(c_h, c_s, s_h, s_s, num_bins: int = 12, min_pixels: int = 100) -> torch.Tensor:
+    """color_fix.py:698-741: per 30-degree hue bin; bin 0 also takes hue >= 11/12 (red wrap-around), and bin 11 then
+    re-matches those same pixels from the ORIGINAL saturations (the reference's loop overwrites them)."""
+    bw = 1.0 / num_bins
+    out = c_s.clone()
+    for b in range(num_bins):
+        lo, hi = b * bw, (b + 1) * bw
+        if b == 0:
+            cm = ((c_h >= 0) & (c_h < hi)) | (c_h >= (1.0 - bw))
+            sm = ((s_h >= 0) & (s_h < hi)) | (s_h >= (1.0 - bw))
+        else:
+            cm, sm = (c_h >= lo) & (c_h < hi), (s_h >= lo) & (s_h < hi)
+        cs, ss = c_s[cm], s_s[sm]
+        if cs.numel() > min_pixels and ss.numel() > min_pixels:
+            out[cm] = histogram_match_1d(cs, ss)
+    return out
+
+
+def hsv_saturation_histogram_match(content: torch.Tensor, style: torch.Tensor, out_bf16: bool = True) -> torch.Tensor:
+    """color_fix.py:524-611 for equal shapes (fp32 inside; result cast to the input dtype)."""
+    c01 = ((content.float() + 1.0) * 0.5).clamp(0.0, 1.0)
+    s01 = ((style.float() + 1.0) * 0.5).clamp(0.0, 1.0)
+    c_hsv, s_hsv = rgb_to_hsv(c01), rgb_to_hsv(s01)
+    m_s = hue_conditional_saturation_match(c_hsv[:, 0], c_hsv[:, 1], s_hsv[:, 0], s_hsv[:, 1])
+    rgb = hsv_to_rgb(torch.stack([c_hsv[:, 0], m_s, c_hsv[:, 2]], 1)).clamp(0.0, 1.0)
+    res = rgb * 2.0 - 1.0
+    return res.to(torch.bfloat16).float() if out_bf16 else res
+
+
+def saturation_map(x: torch.Tensor) -> torch.Tensor:
+    """color_fix.py:858-872."""
+    rgb = ((x + 1.0) * 0.5).clamp(0.0, 1.0)
+    maxc, minc = rgb.max(1, keepdim=True).values, rgb.min(1, keepdim=True).values
+    return torch.where(maxc > 1e-10, (maxc - minc) / maxc.clamp(min=1e-10), torch.zeros_like(maxc))
+
+
+def wavelet_adaptive_color_correction(content: torch.Tensor, style: torch.Tensor) -> torch.Tensor:
+    """color_fix.py:772-855: everything in fp32 (inputs are cast first, so the wavelet pass does NOT round to bf16
+    here), HSV result blended into the wavelet result where the content is over-saturated."""
+    c, s = content.float(), style.float()
+    wav = wavelet_reconstruction(c, s, mode="fp32")
+    hsv = hsv_saturation_histogram_match(c, s, out_bf16=False)
+    c_sat, s_sat, w_sat = saturation_map(c), saturation_map(s), saturation_map(wav)
+    weight = torch.sigmoid(5.0 * ((c_sat - s_sat) - 0.15))
+    weight = (weight * ((w_sat - s_sat) > (0.15 * 0.5)).float()).clamp(0.0, 1.0)
+    return (wav * (1.0 - weight) + hsv * weight).to(content.dtype).float()

@@ -190,6 +190,25 @@ def run_color_cases():
         psnr = 99.0 if mse == 0 else 10 * np.log10(4.0 / mse)
         assert same > 0.99 and psnr > 60.0, (name, same, psnr)
         print(f"{name}: wavelet/adain oracle == reference (bit-exact); lab {100 * same:.2f}% equal, {psnr:.1f} dB")
+        if name == "color_t2_40x56":
+            # hsv / wavelet_adaptive (not shipped by the engine yet): saturation has heavy ties (a third of the values),
+            # so the reference's unstable sort leaves the result defined only up to the tie order — pin the colour-space
+            # conversions bit for bit and the result as a distribution.
+            tint = torch.tensor([1.0, 0.6, 0.3]).view(1, 3, 1, 1)
+            c2, s2 = (content.float() * tint).to(torch.bfloat16), (style.float() * tint * 0.9).to(torch.bfloat16)
+            c01 = ((c2.float() + 1.0) * 0.5).clamp(0.0, 1.0)
+            assert torch.equal(ref._rgb_to_hsv_batch(c01.clone()), co.rgb_to_hsv(c01))
+            assert torch.equal(ref._hsv_to_rgb_batch(co.rgb_to_hsv(c01)), co.hsv_to_rgb(co.rgb_to_hsv(c01)))
+            outs["hsv"] = ref.hsv_saturation_histogram_match(c2.clone(), s2.clone(), _Dbg())
+            outs["wavelet_adaptive"] = ref.wavelet_adaptive_color_correction(c2.clone(), s2.clone(), _Dbg())
+            for key, fn in (("hsv", co.hsv_saturation_histogram_match), ("wavelet_adaptive", co.wavelet_adaptive_color_correction)):
+                o = fn(c2, s2)
+                sat = lambda x: co.saturation_map(x.float()).flatten().sort().values
+                dsat = (sat(o) - sat(outs[key])).abs()
+                db = 10 * np.log10(4.0 / ((o - outs[key].float()) ** 2).mean().item())
+                print(f"   {key}: sorted-saturation diff max {dsat.max().item():.4f} mean {dsat.mean().item():.5f}, {db:.1f} dB")
+                assert dsat.mean() < 2e-3 and db > 35.0, key
+            print(f"{name}: hsv / wavelet_adaptive oracle == reference as distributions (tie order is unspecified)")
         np.savez_compressed(os.path.join(GOLD, name + ".npz"),
                             **{k: v.float().numpy().astype(np.float32) for k, v in outs.items()})
     # temporal-overlap cross-fade (src/core/generation_utils.py:284-312), bit for bit for every overlap length
