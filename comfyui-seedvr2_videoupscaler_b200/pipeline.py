@@ -28,6 +28,27 @@ def pad_4n1(n: int) -> int:
     return n if n % 4 == 1 else n + (4 - (n - 1) % 4)
 
 
+def pad_video_temporal(frames: torch.Tensor, count: int = 0, prepend: bool = False) -> torch.Tensor:
+    """Temporal padding along dim 0 with REVERSED frames, the reference's single source of truth for the 4n+1
+    constraint and for prepended frames (``pad_video_temporal``, generation_utils.py:598-657): ``count == 0`` pads the
+    end up to the next 4n+1; the mirror excludes the edge frame itself ([f0..f7] -> [f0..f7, f6]); when more frames
+    are needed than the clip has, the far-edge frame is repeated."""
+    t = frames.shape[0]
+    if count == 0 and not prepend:
+        if t % 4 == 1:
+            return frames
+        count = ((t - 1) // 4 + 1) * 4 + 1 - t
+    if count <= 0:
+        return frames
+    if count >= t:
+        last = frames[-1:]
+        repeated = last.expand(count - t + 1, *frames.shape[1:])
+        rev = frames[1:].flip(0) if t > 1 else last[:0]
+        return torch.cat([repeated, rev, frames] if prepend else [frames, rev, repeated], 0)
+    rev = frames[1:count + 1].flip(0) if prepend else frames[-count - 1:-1].flip(0)
+    return torch.cat([rev, frames] if prepend else [frames, rev], 0)
+
+
 class SeedVR2Engine:
     def __init__(self, dit_cfg: dict, dit_sd: Dict[str, torch.Tensor], vae_sd: Dict[str, torch.Tensor],
                  txt_embed: torch.Tensor, device="cuda"):
@@ -85,8 +106,7 @@ class SeedVR2Engine:
         T0 = frames.shape[0]
         x = frames.to(self.device)
         T = pad_4n1(T0)
-        if T > T0:
-            x = torch.cat([x, x[-1:].expand(T - T0, -1, -1, -1)], 0)
+        x = pad_video_temporal(x)                                   # mirrored tail frames, generation_phases.py:109-124
         # resize (identity when the frames already have the target size) + clamp + pad-16 + normalise + c t h w
         # in one kernel (prepare_video_transforms, generation_utils.py:72-84)
         res = resolution if resolution is not None else min(frames.shape[1], frames.shape[2])

@@ -231,6 +231,23 @@ def run_color_cases():
         assert ref_out.dtype == torch.float32 and torch.equal(ref_out, co.blend_overlapping_frames(a, b, ov)), ov
         blends[f"f32_ov{ov}"] = ref_out.numpy()
     print("blend_overlapping_frames: oracle == reference (bit-exact) for overlaps 1,2,3,4,7,8 (bf16) and 2,5 (fp32)")
+    # temporal padding with reversed frames (src/core/generation_utils.py:598-657): frame-index sequences
+    start = gu_src.index("def pad_video_temporal")
+    exec(gu_src[start:gu_src.index("\ndef ", start + 10)], ns)
+    ns.setdefault("Optional", __import__("typing").Optional)
+    pads = {}
+    for t in range(1, 14):
+        idx = torch.arange(t, dtype=torch.float32).view(1, t, 1, 1)                 # c t h w, value = frame index
+        auto = ns["pad_video_temporal"](idx, temporal_dim=1)
+        assert torch.equal(auto, vae_oracle.pad_video_temporal(idx, temporal_dim=1)), t
+        pads[f"auto_t{t}"] = auto.flatten().numpy()
+        for count in (1, 3, t, t + 2):
+            for prepend in (False, True):
+                r = ns["pad_video_temporal"](idx, count=count, temporal_dim=1, prepend=prepend)
+                assert torch.equal(r, vae_oracle.pad_video_temporal(idx, count, 1, prepend)), (t, count, prepend)
+                pads[f"t{t}_c{count}_{'pre' if prepend else 'app'}"] = r.flatten().numpy()
+    print("pad_video_temporal: oracle == reference for t = 1..13, explicit counts, append / prepend")
+    np.savez_compressed(os.path.join(GOLD, "pad_temporal.npz"), **pads)
     np.savez_compressed(os.path.join(GOLD, "blend_overlap.npz"), **blends)
 
 

@@ -172,3 +172,24 @@ def runner_decode(sd, lat, mode="fp32"):
     z = lat.permute(3, 0, 1, 2)[None]
     z = z / SCALING_FACTOR + SHIFTING_FACTOR
     return vae_decode(sd, z, mode)
+
+
+def pad_video_temporal(videos: torch.Tensor, count: int = 0, temporal_dim: int = 0, prepend: bool = False) -> torch.Tensor:
+    """generation_utils.py:598-657: temporal padding with reversed frames (4n+1 constraint when count == 0)."""
+    t = videos.size(temporal_dim)
+    if count == 0 and not prepend:
+        if t % 4 == 1:
+            return videos
+        count = ((t - 1) // 4 + 1) * 4 + 1 - t
+    if count <= 0:
+        return videos
+    v = videos.movedim(temporal_dim, 0)
+    if count >= t:
+        last = v[-1:]
+        repeated = last.repeat(count - t + 1, *([1] * (v.ndim - 1)))
+        rev = v[1:].flip(0) if t > 1 else last[:0]
+        out = torch.cat([repeated, rev, v] if prepend else [v, rev, repeated], 0)
+    else:
+        rev = v[1:count + 1].flip(0) if prepend else v[-count - 1:-1].flip(0)
+        out = torch.cat([rev, v] if prepend else [v, rev], 0)
+    return out.movedim(0, temporal_dim)

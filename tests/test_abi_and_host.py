@@ -162,3 +162,21 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "upscaled frames/sec SeedVR2-3B 720p->4K" and d["unit"] == "frames/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_temporal_padding_mirrors_frames_like_the_reference(pkg):
+    """pad_video_temporal (generation_utils.py:598-657): the 4n+1 padding appends REVERSED frames (excluding the edge
+    frame), not copies of the last frame; goldens are frame-index sequences produced by the reference function."""
+    import numpy as np
+    pipeline = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.pipeline")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "pad_temporal.npz"))
+    for t in range(1, 14):
+        frames = torch.arange(t, dtype=torch.float32).view(t, 1, 1, 1)          # t h w c, value = frame index
+        out = pipeline.pad_video_temporal(frames)
+        assert out.shape[0] == pipeline.pad_4n1(t)
+        assert out.flatten().tolist() == gold[f"auto_t{t}"].tolist()
+        for count in (1, 3, t, t + 2):
+            for prepend in (False, True):
+                r = pipeline.pad_video_temporal(frames, count=count, prepend=prepend)
+                assert r.flatten().tolist() == gold[f"t{t}_c{count}_{'pre' if prepend else 'app'}"].tolist()
+    assert pipeline.pad_video_temporal(torch.arange(8.).view(8, 1, 1, 1)).flatten().tolist() == [0, 1, 2, 3, 4, 5, 6, 7, 6]
