@@ -6,7 +6,7 @@ decoded frames — replacing the reference's mp.Queue + shared-memory + numpy ha
 (``inference_cli.py:1100, 1227-1232``).  The partition is the reference's:
 ``total // n`` frames per rank, +1 for the first ``total % n`` ranks, plus
 ``temporal_overlap`` extra frames on all but the last rank
-(``inference_cli.py:1166-1176``).
+(``inference_cli.py:1166-1176``; ``partition_preloaded`` is the variant for frames already in memory, ``:1196-1213``).
 """
 from __future__ import annotations
 
@@ -26,6 +26,30 @@ def partition_frames(total: int, n: int, overlap: int = 0, start: int = 0) -> Li
             end = min(end + overlap, start + total)
         out.append((cur, end))
         cur += cnt
+    return out
+
+
+def partition_preloaded(total: int, n: int, overlap: int = 0, batch_size: int = 1) -> List[Tuple[int, int]]:
+    """[start, end) per rank when the whole frame tensor is already in memory (inference_cli.py:1196-1213): without
+    overlap ``torch.chunk`` (ceil(total / n) frames per rank, the tail ranks may get fewer or none); with overlap,
+    chunks of ``total // n + overlap`` frames rounded up to a multiple of ``batch_size``, stepping by that minus the
+    overlap, the last rank running to the end."""
+    if overlap > 0 and n > 1:
+        cwo = total // n + overlap
+        if batch_size > 1:
+            cwo = (cwo + batch_size - 1) // batch_size * batch_size
+        base = cwo - overlap
+        out = []
+        for i in range(n):
+            s = i * base
+            e = total if i == n - 1 else min(s + cwo, total)
+            out.append((min(s, total), max(min(s, total), e)))
+        return out
+    size = -(-total // n)          # torch.chunk
+    out, cur = [], 0
+    while cur < total:
+        out.append((cur, min(cur + size, total)))
+        cur += size
     return out
 
 

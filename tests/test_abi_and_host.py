@@ -180,3 +180,23 @@ def test_temporal_padding_mirrors_frames_like_the_reference(pkg):
                 r = pipeline.pad_video_temporal(frames, count=count, prepend=prepend)
                 assert r.flatten().tolist() == gold[f"t{t}_c{count}_{'pre' if prepend else 'app'}"].tolist()
     assert pipeline.pad_video_temporal(torch.arange(8.).view(8, 1, 1, 1)).flatten().tolist() == [0, 1, 2, 3, 4, 5, 6, 7, 6]
+
+
+def test_partition_preloaded_matches_reference_chunking(pkg):
+    """inference_cli.py:1196-1213 restated literally (torch.chunk / chunk-with-overlap) vs shard.partition_preloaded."""
+    shard = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.shard")
+    for total in (1, 5, 16, 23, 64, 97):
+        frames = torch.arange(total)
+        for n in (1, 2, 3, 4, 8):
+            for overlap in (0, 2, 4):
+                for bs in (1, 5):
+                    if overlap > 0 and n > 1:
+                        cwo = total // n + overlap
+                        if bs > 1:
+                            cwo = ((cwo + bs - 1) // bs) * bs
+                        base = cwo - overlap
+                        ref = [frames[i * base: (total if i == n - 1 else min(i * base + cwo, total))] for i in range(n)]
+                    else:
+                        ref = list(torch.chunk(frames, n, dim=0))
+                    got = shard.partition_preloaded(total, n, overlap, bs)
+                    assert [frames[a:b].tolist() for a, b in got] == [r.tolist() for r in ref], (total, n, overlap, bs)
