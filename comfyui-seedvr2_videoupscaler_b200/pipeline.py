@@ -103,16 +103,26 @@ class SeedVR2Engine:
         are already at the target resolution).  Returns (T,H,W,3) bf16 in [0,1] on the device.
         ``color_correction``: "none", "lab" (the reference CLI default), "wavelet" or "adain" — matched against the
         transformed input clip (generation_phases.py:1299-1317)."""
+        sample, style = self.clip_to_sample(frames, noise=noise, seed=seed, resolution=resolution,
+                                            max_resolution=max_resolution)
+        if color_correction != "none":
+            sample = color_fix.apply_color_correction(sample, style, color_correction)
+        return color_fix.sample_to_image(sample)                    # t h w c in [0,1]
+
+    @torch.no_grad()
+    def clip_to_sample(self, frames: torch.Tensor, noise: Optional[torch.Tensor] = None, seed: int = 42,
+                       resolution: Optional[int] = None, max_resolution: int = 0):
+        """Phases 1-3 for one clip: frames (T,h,w,3) in [0,1] -> (sample, style), both (T,3,H,W) bf16 in [-1,1]:
+        the decoded clip and the transformed input clip it is colour-matched against in phase 4."""
         T0 = frames.shape[0]
         x = frames.to(self.device)
-        T = pad_4n1(T0)
         x = pad_video_temporal(x)                                   # mirrored tail frames, generation_phases.py:109-124
         # resize (identity when the frames already have the target size) + clamp + pad-16 + normalise + c t h w
         # in one kernel (prepare_video_transforms, generation_utils.py:72-84)
         res = resolution if resolution is not None else min(frames.shape[1], frames.shape[2])
         tf = preprocess.VideoTransform(res, max_resolution)
         H0, W0 = tf.true_size(frames.shape[1], frames.shape[2])
-        x = tf.run(x, channels_last=True)                          # (3, T, Hp, Wp) bf16 in [-1,1]
+        x = tf.run(x, channels_last=True)                           # (3, T, Hp, Wp) bf16 in [-1,1]
         latent = self.vae_encode(x)
         if noise is None:
             g = torch.Generator(device=self.device).manual_seed(seed)
@@ -120,10 +130,75 @@ class SeedVR2Engine:
         x0 = self.inference(noise, latent)
         y = self.vae_decode(x0)                                     # (3,T,H,W)
         sample = y[:, :T0, :H0, :W0].permute(1, 0, 2, 3)            # t c h w, the layout of phase 4
-        if color_correction != "none":
-            style = x[:, :T0, :H0, :W0].permute(1, 0, 2, 3)        # the transformed input clip in [-1,1]
-            sample = color_fix.apply_color_correction(sample, style, color_correction)
-        return color_fix.sample_to_image(sample)                    # t h w c in [0,1]
+        style = x[:, :T0, :H0, :W0].permute(1, 0, 2, 3)            # the transformed input clip in [-1,1]
+        return sample, style
+
+    @torch.no_grad()
+    def upscale_video(self, frames: torch.Tensor, batch_size: int = 5, temporal_overlap: int = 0, seed: int = 42,
+                      color_correction: str = "none", resolution: Optional[int] = None,
+                      max_resolution: int = 0) -> torch.Tensor:
+        """A whole video on one GPU the way the reference's four phases do it (generation_phases.py:271-289, 344-358,
+        969-1000, 1236-1345): batches of ``batch_size`` frames stepping by ``batch_size - temporal_overlap``, every batch
+        seeded identically, the overlap cross-faded into the previous batch's tail, colour correction per batch
+        against its own input frames, [0,1] image format.  Returns (T,H,W,3) bf16."""
+        from . import shard
+
+        def clip(a, b):
+            s, st = self.clip_to_sample(frames[a:b], seed=seed, resolution=resolution, max_resolution=max_resolution)
+            return s.contiguous(), st.contiguous()
+
+        def post(sample, style):
+            if color_correction != "none":
+                sample = color_fix.apply_color_correction(sample, style, color_correction)
+            return color_fix.sample_to_image(sample)
+
+        return run_batched(frames.shape[0], batch_size, temporal_overlap, clip, shard.blend_overlap, post)
+
+
+
+def batch_ranges(total: int, batch_size: int, temporal_overlap: int = 0):
+    """([start, end) per batch, effective overlap) of generation_phases.py:271-289, 344-358: step =
+    batch_size - overlap (overlap reset to 0 when it is not smaller than the batch); a trailing batch that would hold
+    nothing but overlap frames is dropped."""
+    step = batch_size - temporal_overlap if temporal_overlap > 0 else batch_size
+    if step <= 0:
+        step, temporal_overlap = batch_size, 0
+    out = []
+    for idx in range(0, total, step):
+        end = min(idx + batch_size, total)
+        if idx > 0 and end - idx <= temporal_overlap:
+            break
+        out.append((idx, end))
+    return out, temporal_overlap
+
+
+def run_batched(total: int, batch_size: int, temporal_overlap: int, clip_fn, blend_fn, post_fn) -> torch.Tensor:
+    """The reference's batch loop with the engine plugged in as callables: ``clip_fn(start, end) -> (sample, style)``
+    ((t,3,H,W) in [-1,1]), ``blend_fn(prev_tail, cur_head)``, ``post_fn(sample, style) -> (t,H,W,3)``.  Decoded batches are
+    laid end to end; from the second batch on the first ``overlap`` frames are cross-faded into the tail already written
+    and dropped (generation_phases.py:969-1000), and phase 4 then post-processes every batch's slice against its own
+    input frames minus those overlap frames (:1249-1263)."""
+    ranges, overlap = batch_ranges(total, batch_size, temporal_overlap)
+    samples, styles = [], []
+    written = 0
+    for i, (a, b) in enumerate(ranges):
+        sample, style = clip_fn(a, b)
+        if i > 0 and overlap > 0 and overlap < sample.shape[0] and written >= overlap:
+            # the tail lives in the previous batches' slices (it may span more than one when batches are short)
+            tail = torch.cat(samples, 0)[-overlap:] if samples[-1].shape[0] < overlap else samples[-1][-overlap:]
+            blended = blend_fn(tail.contiguous(), sample[:overlap].contiguous())
+            k = overlap
+            for j in range(len(samples) - 1, -1, -1):          # write the blended frames back, last slice first
+                n = min(k, samples[j].shape[0])
+                samples[j][samples[j].shape[0] - n:] = blended[k - n:k].to(samples[j].dtype)
+                k -= n
+                if k == 0:
+                    break
+            sample, style = sample[overlap:], style[overlap:]
+        samples.append(sample)
+        styles.append(style[: sample.shape[0]])
+        written += sample.shape[0]
+    return torch.cat([post_fn(s_, st_) for s_, st_ in zip(samples, styles)], 0)
 
 
 class GraphedClip:

@@ -200,3 +200,93 @@ def test_partition_preloaded_matches_reference_chunking(pkg):
                         ref = list(torch.chunk(frames, n, dim=0))
                     got = shard.partition_preloaded(total, n, overlap, bs)
                     assert [frames[a:b].tolist() for a, b in got] == [r.tolist() for r in ref], (total, n, overlap, bs)
+
+
+def test_batched_video_loop_matches_reference_phases(pkg):
+    """pipeline.batch_ranges / run_batched vs a literal restatement of the reference's loops: batch indices
+    (generation_phases.py:271-289, 344-358), overlap cross-fade into the already written tail and trimming (:969-1000),
+    per-batch post-processing against the input frames minus the overlap (:1249-1263)."""
+    from oracle import color_oracle
+    pipeline = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.pipeline")
+    blend = lambda p, c: color_oracle.blend_overlapping_frames(p, c, p.shape[0]).to(torch.bfloat16)
+    for total, bs, ov in ((23, 5, 0), (23, 5, 2), (17, 9, 4), (12, 5, 3), (9, 5, 4), (6, 5, 7), (5, 5, 2), (30, 13, 1)):
+        g = torch.Generator().manual_seed(total * 100 + bs * 10 + ov)
+        frames = torch.rand(total, 3, 4, 8, generator=g).to(torch.bfloat16)               # stands for the input clip
+        decoded = {}
+
+        def clip(a, b):
+            if (a, b) not in decoded:
+                decoded[(a, b)] = torch.rand(b - a, 3, 4, 8, generator=g).to(torch.bfloat16)
+            return decoded[(a, b)].clone(), frames[a:b].clone()
+
+        post = lambda smp, sty: (smp.float() * 0.5 + sty.float() * 0.25).permute(0, 2, 3, 1)
+        got = pipeline.run_batched(total, bs, ov, clip, blend, post)
+        # ---- reference restatement
+        step = bs - ov if ov > 0 else bs
+        eff = ov
+        if step <= 0:
+            step, eff = bs, 0
+        ranges = []
+        for idx in range(0, total, step):
+            end = min(idx + bs, total)
+            if idx > 0 and end - idx <= eff:
+                break
+            ranges.append((idx, end))
+        assert pipeline.batch_ranges(total, bs, ov) == (ranges, eff)
+        final = torch.zeros(0, 3, 4, 8, dtype=torch.bfloat16)
+        slices = []
+        for i, (a, b) in enumerate(ranges):
+            smp = decoded[(a, b)].clone()
+            start = final.shape[0]
+            if i > 0 and eff > 0 and eff < smp.shape[0] and start >= eff:
+                final[start - eff:start] = blend(final[start - eff:start], smp[:eff])
+                smp = smp[eff:]
+            final = torch.cat([final, smp], 0)
+            slices.append((start, final.shape[0], a, i))
+        outs = []
+        for start, stop, a, i in slices:
+            sty = frames[a:a + bs][(eff if i > 0 else 0):][: stop - start]
+            outs.append(post(final[start:stop], sty))
+        ref = torch.cat(outs, 0)
+        assert got.shape == ref.shape and torch.equal(got, ref), (total, bs, ov)
+        if eff < bs:
+            assert got.shape[0] == total or ranges[-1][1] < total
+
+
+def test_clip_runner_control_flow_with_stubbed_kernels(pkg, monkeypatch):
+    """upscale_clip / clip_to_sample / upscale_video sequencing on CPU with the GPU stages stubbed (the kernels are
+    covered by the -m gpu tests): shapes, cropping, padding, batching and the colour-correction hook."""
+    pipeline = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.pipeline")
+    preprocess = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.preprocess")
+    color_fix = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.color_fix")
+    shard = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.shard")
+    eng = object.__new__(pipeline.SeedVR2Engine)
+    eng.device = torch.device("cpu")
+    seen = {}
+
+    def fake_run(self, x, channels_last):                                  # (T,h,w,3) -> (3,T,Hp,Wp), 2x nearest up-scale
+        (H, W), _ = preprocess.resized_size(x.shape[1], x.shape[2], self.resolution, self.max_resolution)
+        y = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2).float(), size=(H, W)).permute(1, 0, 2, 3)
+        y = torch.nn.functional.pad(y, (0, (16 - W % 16) % 16, 0, (16 - H % 16) % 16))
+        seen["frames_in"] = x.shape[0]
+        return (y * 2 - 1).to(torch.bfloat16)
+
+    monkeypatch.setattr(preprocess.VideoTransform, "run", fake_run)
+    eng.vae_encode = lambda x: torch.zeros((x.shape[1] - 1) // 4 + 1, x.shape[2] // 8, x.shape[3] // 8, 16, dtype=torch.bfloat16)
+    eng.inference = lambda noise, latent: noise
+    eng.vae_decode = lambda z: torch.ones(3, 4 * z.shape[0] - 3, 8 * z.shape[1], 8 * z.shape[2], dtype=torch.bfloat16) * 0.5
+    monkeypatch.setattr(color_fix, "apply_color_correction", lambda s_, st, mode, debug=None: (s_.float() * 0 + st.float()).to(torch.bfloat16))
+    monkeypatch.setattr(color_fix, "sample_to_image", lambda s_: (s_.float().permute(0, 2, 3, 1).clamp(-1, 1) * 0.5 + 0.5).to(torch.bfloat16))
+    monkeypatch.setattr(shard, "blend_overlap", lambda p, c: ((p.float() + c.float()) / 2).to(p.dtype))
+    frames = torch.rand(6, 20, 30, 3)
+    out = eng.upscale_clip(frames, resolution=40)
+    assert out.shape == (6, 40, 60, 3) and seen["frames_in"] == 9           # 6 -> 9 frames (4n+1), cropped back to 6
+    assert torch.allclose(out.float(), torch.full_like(out.float(), 0.75))
+    out = eng.upscale_clip(frames, resolution=40, color_correction="lab")    # colour hook receives the transformed input
+    ref = torch.nn.functional.interpolate(frames.permute(0, 3, 1, 2), size=(40, 60)).permute(0, 2, 3, 1)
+    assert out.shape == (6, 40, 60, 3) and (out.float() - ref).abs().max() < 0.02
+    smp, sty = eng.clip_to_sample(frames[:5], resolution=40)
+    assert smp.shape == sty.shape == (5, 3, 40, 60) and seen["frames_in"] == 5
+    vid = eng.upscale_video(torch.rand(13, 20, 30, 3), batch_size=5, temporal_overlap=2, resolution=40)
+    assert vid.shape == (13, 40, 60, 3)
+    assert tuple(eng.latent_shape(frames, 40)) == (3, 6, 8, 16)
