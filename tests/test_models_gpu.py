@@ -189,6 +189,25 @@ def test_pipeline_resize_color_and_cuda_graph(pkg):
     assert torch.equal(gc(frames), eager1)
 
 
+def test_upscale_video_batches_and_overlap(pkg):
+    """Whole-video loop (generation_phases.py batching): one batch == upscale_clip bit for bit; with overlap the frames
+    before the first cross-fade are those of the first batch; the output covers every input frame."""
+    pipeline = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.pipeline")
+    dit = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.dit")
+    cfg = dit.dit_config("3b", dim=256, heads=2, layers=2, mm_layers=1, txt_in_dim=64)
+    eng = pipeline.SeedVR2Engine(cfg, pkg.weights.synth_dit_state_dict(cfg, seed=1),
+                                 pkg.weights.synth_vae_state_dict(seed=2), torch.randn(58, 64))
+    frames = torch.rand(13, 36, 52, 3, generator=torch.Generator().manual_seed(2)).cuda()
+    kw = dict(resolution=72, color_correction="wavelet")
+    one = eng.upscale_video(frames[:5], batch_size=5, **kw)
+    assert torch.equal(one, eng.upscale_clip(frames[:5], **kw))
+    vid = eng.upscale_video(frames, batch_size=5, temporal_overlap=2, **kw)
+    assert vid.shape == (13, 72, 104, 3) and torch.isfinite(vid).all() and 0 <= vid.min() and vid.max() <= 1
+    plain = eng.upscale_video(frames, batch_size=5, temporal_overlap=0, **kw)
+    assert plain.shape == (13, 72, 104, 3)
+    assert torch.equal(plain[:5], one)                        # without overlap the first batch is untouched
+
+
 def test_vae_medium_size_vs_oracle(vae_pair):
     """Larger spatial size than the goldens (ragged tile edges, CTA-pair / swap-AB / fused-statistics paths):
     engine vs the oracle run on the same GPU in fp32 and in the reference's bf16 flow."""
