@@ -43,6 +43,10 @@ WORKLOADS = {
     "720p": (8, 720, 1280, "SeedVR2-3B bf16, 8-frame (->9) 360p->720p clip (smoke)"),
     "tiny": (4, 128, 192, "tiny clip (smoke)"),
 }
+# BASELINE config 5: VAE-only decode of a latent (T, 90, 160) -> (4T-3) frames of 720 x 1280, `--workload vae_decode_T<T>`
+for _t in (16, 32, 64, 128):
+    WORKLOADS[f"vae_decode_T{_t}"] = (4 * _t - 3, 720, 1280, f"VAE-only 3D-conv decode, latent T={_t} x 90 x 160 -> "
+                                                               f"{4 * _t - 3} frames 720x1280 = BASELINE config 5")
 DEFAULT_WORKLOAD = "4k_shard"
 
 
@@ -153,13 +157,44 @@ def run_reference_arm(args, frames_real, frames_pad, H, W, workload_desc):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_desc, "note": "reference PyTorch path restated by oracle/ (the reference "
                        "itself cannot be installed: diffusers/omegaconf/rotary_embedding_torch absent); CPU fp32"},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": info["cores"], "kind": "port",
-                             "sample": info["sample"]},
+            "extrapolated": True,
+            "cpu_baseline": {"value": float(f"{v:.2g}"), "unit": "frames/s", "cores": info["cores"], "kind": "port",
+                             "extrapolated": True, "sample": info["sample"]},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------
+# per-kernel table: C-ABI entry point -> (bound, what the profiler's flops / bytes annotation means)
+HBM_KERNELS = {"svr2_groupnorm_from_stats_bf16", "svr2_groupnorm_bf16", "svr2_rmsnorm_ada_bf16", "svr2_conv_tap_gather",
+               "svr2_qk_norm_rope_window_bf16", "svr2_resize_bicubic_aa_bf16", "svr2_sample_to_image_bf16",
+               "svr2_txt_window_mean_bf16", "svr2_im2col3_bf16", "svr2_ncdhw_to_ndhwc_bf16", "svr2_transpose_bf16"}
+
+
+def kernel_table(prof, steps, peak_tf, peak_gbs, step_ms):
+    """[{name, ms, share, bound, achieved, unit, frac}] per C-ABI entry point, largest first (algorithmic FLOPs or bytes
+    of all its launches / their CUDA-event time, against the measured tensor / HBM peak)."""
+    agg = {}
+    for n, d in prof.items():
+        a = agg.setdefault(n.split("|")[0], dict(ms=0.0, flops=0.0, bytes=0.0, calls=0))
+        for k in ("ms", "flops", "bytes", "calls"):
+            a[k] += d[k]
+    rows = []
+    for n, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        row = {"name": n, "calls_per_step": a["calls"] // steps, "ms": round(a["ms"] / steps, 3),
+               "share": round(a["ms"] / steps / step_ms, 4)}
+        if a["flops"] > 0:
+            ach = a["flops"] / a["ms"] / 1e9
+            row.update(bound="tensor", achieved=round(ach, 1), unit="TFLOP/s", frac=round(ach / peak_tf, 3))
+        elif a["bytes"] > 0:
+            ach = a["bytes"] / a["ms"] / 1e6
+            row.update(bound="hbm", achieved=round(ach, 1), unit="GB/s", frac=round(ach / peak_gbs, 3))
+        else:
+            row.update(bound="hbm" if n in HBM_KERNELS else "latency", achieved=None, unit=None, frac=None)
+        rows.append(row)
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,6 +203,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lib-baseline", default="default", choices=["none", "ops", "default", "full"],
+                    help="time the reference's GPU libraries beside the engine (tools/gpu_library_baseline.py): ops = "
+                         "flash-attn-2 / SDPA, cuBLAS, cuDNN on the 4K-shard shapes; default = ops + the reference's bf16 "
+                         "library flow per phase at BASELINE config 2; full = + the 4K shard (N = 1, rank 0 only)")
     ap.add_argument("--source", default="lowres", choices=["lowres", "target"],
                     help="lowres: the clip enters at its source resolution (H/3 x W/3 for 720p->4K, H/2 x W/2 for "
                          "540p->1080p) and is resized on the device by the pre-processing kernel, as in the "
@@ -181,6 +220,7 @@ def main():
     ap.add_argument("--detail", action="store_true", help="with --phases: break GEMM/conv launches down by shape")
     args = ap.parse_args()
     frames_real, H, W, desc = WORKLOADS[args.workload]
+    vae_only = args.workload.startswith("vae_decode")
     from svr2_import import load_package
     pkg = load_package()
     import importlib
@@ -204,16 +244,25 @@ def main():
     variant = "7b" if args.workload.endswith("_7b") else "3b"
     eng = pipeline.build_synthetic_engine(variant, device=dev)
     # source clip: 720p for the 4K shard (x3), 540p for 1080p (x2), half size otherwise
-    div = 1 if args.source == "target" else (3 if H == 2160 else 2)
-    frames_host = synth_frames(frames_real, H // div, W // div, seed=42 + rank).to(torch.bfloat16).pin_memory()
+    div = 1 if (args.source == "target" or vae_only) else (3 if H == 2160 else 2)
+    if vae_only:        # config 5: the step is one decode of a synthetic latent (T, 90, 160, 16), scaled like the runner's
+        T_lat = (frames_real + 3) // 4
+        g = torch.Generator().manual_seed(42 + rank)
+        frames_host = (torch.randn(T_lat, H // 8, W // 8, 16, generator=g) * 0.9152).to(torch.bfloat16).pin_memory()
+        out_host = torch.empty(3, frames_real, H, W, dtype=torch.bfloat16).pin_memory()
+    else:
+        frames_host = synth_frames(frames_real, H // div, W // div, seed=42 + rank).to(torch.bfloat16).pin_memory()
+        out_host = torch.empty(frames_real, H, W, 3, dtype=torch.bfloat16).pin_memory()
     frames_dev = frames_host.to(dev)
-    out_host = torch.empty(frames_real, H, W, 3, dtype=torch.bfloat16).pin_memory()
-    gather_buf = torch.empty(world, frames_real, H, W, 3, device=dev, dtype=torch.bfloat16) if world > 1 else None
+    gather_buf = torch.empty((world,) + tuple(out_host.shape), device=dev, dtype=torch.bfloat16) if world > 1 else None
     # a buffer larger than L2 (126 MB) written between steps is unnecessary: every step streams > 10 GB of activations
     noise = None
 
     def step(src):
-        y = eng.upscale_clip(src, noise=noise, seed=42, color_correction=args.color_correction, resolution=H)
+        if vae_only:
+            y = eng.vae_decode(src)
+        else:
+            y = eng.upscale_clip(src, noise=noise, seed=42, color_correction=args.color_correction, resolution=H)
         if world > 1:
             dist.all_gather_into_tensor(gather_buf.view(-1), y.reshape(-1).contiguous())
         return y
@@ -244,11 +293,28 @@ def main():
     launches = lib.LAUNCHES
     prof = lib.PROFILER.summary()
     lib.PROFILER = None
+    # ---- "DiT step ms" (BASELINE.json metric, second half): one NaDiT forward (+ the x0 = noise - v endpoint) at this
+    # workload's latent geometry, CUDA events, inputs resident
+    dit_step_ms = None
+    if not vae_only:
+        lshape = eng.latent_shape(frames_dev, H)
+        lat = torch.randn(lshape, device=dev, dtype=torch.bfloat16)
+        nz = torch.randn(lshape, device=dev, dtype=torch.bfloat16)
+        eng.inference(nz, lat)
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(3):
+            eng.inference(nz, lat)
+        d1.record()
+        torch.cuda.synchronize()
+        dit_step_ms = d0.elapsed_time(d1) / 3
+        del lat, nz
     # ---- timed region B: end to end with host buffers.  On one GPU the clip is replayed as ONE CUDA graph
     # (SeedVR2Engine.graphed: same kernels, same results, no per-launch host work, so a busy host cannot stall the
     # GPU); any capture problem falls back to eager launches and is reported in the JSON line.
     graphed, graph_note = None, "eager launches"
-    if world == 1 and not args.no_graph:
+    if world == 1 and not args.no_graph and not vae_only:
         try:
             graphed = eng.graphed(frames_dev, seed=42, warmup=0, color_correction=args.color_correction, resolution=H)
             graph_note = "CUDA-graph replay of the clip"
@@ -270,6 +336,9 @@ def main():
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     sampler.stop_flag = True
+    peak_mem = torch.cuda.max_memory_allocated()
+    del graphed
+    torch.cuda.empty_cache()
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -289,6 +358,7 @@ def main():
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_gbs = peaks.get("hbm_gbs", 6500.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     gemm_names = ("svr2_linear_bf16", "svr2_conv3d_bf16", "svr2_conv3d_stats_bf16", "svr2_upsample_shuffle_bf16")
     is_gemm = lambda n: n.split("|")[0] in gemm_names
@@ -297,15 +367,18 @@ def main():
     g_calls = sum(d["calls"] for n, d in prof.items() if is_gemm(n))
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
     fm = flop_model(frames_pad, H, W, variant)
-    # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of one representative
-    # launch (profiles/ncu_full_r1.json, conv 256->256 3x3x3 at 2x1080x1920 on the CTA-pair kernel)
+    # DRAM traffic of the dominant kernel: NOT measured in this run (that needs ncu) — taken from the committed
+    # `ncu --set full` capture of one representative launch and labelled as such; null when the workload does not run it
     traffic, traffic_detail = None, None
     try:
-        cap = json.load(open(os.path.join(ROOT, "profiles", "ncu_full_r1.json")))["conv256_pair"]
-        traffic = (float(cap["dram__bytes_read.sum"]) + float(cap["dram__bytes_write.sum"])) * 1e9   # bytes per launch
-        traffic_detail = {"algorithmic_bytes_per_launch": (4 + 2) * 1080 * 1920 * 256 * 2.0,
-                          "launch": "conv3d 256->256 3x3x3, 2 frames 1080x1920 (+2 halo frames), ncu --set full",
-                          "tensor_pipe_active_pct": float(cap["sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"])}
+        cap_file = next(f for f in ("ncu_full_r2.json", "ncu_full_r1.json") if os.path.exists(os.path.join(ROOT, "profiles", f)))
+        cap = json.load(open(os.path.join(ROOT, "profiles", cap_file)))["conv256_pair"]
+        if H >= 1080 and not args.workload.startswith("image"):
+            traffic = (float(cap["dram__bytes_read.sum"]) + float(cap["dram__bytes_write.sum"])) * 1e9   # bytes per launch
+            traffic_detail = {"source": f"static: profiles/{cap_file} (ncu --set full of one launch, not this run)",
+                              "algorithmic_bytes_per_launch": (4 + 2) * 1080 * 1920 * 256 * 2.0,
+                              "launch": "conv3d 256->256 3x3x3, 2 frames 1080x1920 (+2 halo frames)",
+                              "tensor_pipe_active_pct": float(cap["sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"])}
     except Exception:
         pass
     if args.phases:
@@ -315,12 +388,18 @@ def main():
                 f"{d['bytes'] / d['ms'] / 1e6:8.1f} GB/s" if d["bytes"] else "")
             print(f"  {n:56s} calls {d['calls']:6d}  {d['ms'] / args.steps:9.2f} ms/step  {100 * d['ms'] / tot:5.1f}%  {extra}",
                   file=sys.stderr)
-        print(f"  peak device memory {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", file=sys.stderr)
+        print(f"  peak device memory {peak_mem / 2**30:.1f} GiB", file=sys.stderr)
         print(f"  sum of kernel time {tot / args.steps:.1f} ms/step vs step {ms / args.steps:.1f} ms; model FLOPs/clip "
               f"{(fm['dit'] + fm['enc'] + fm['dec']) / 1e15:.3f} PFLOP", file=sys.stderr)
+    if vae_only:
+        metric = "VAE decode frames/sec (latent T x 90 x 160 -> 720p)"
+        model_flops = fm["dec"]
+    else:
+        metric = ("upscaled frames/sec SeedVR2-3B 720p->4K" if args.workload == "4k_shard"
+                  else f"upscaled frames/sec SeedVR2-{variant.upper()}")
+        model_flops = fm["dit"] + fm["enc"] + fm["dec"]
     line = {
-        "metric": ("upscaled frames/sec SeedVR2-3B 720p->4K" if args.workload == "4k_shard"
-                   else f"upscaled frames/sec SeedVR2-{variant.upper()}"),
+        "metric": metric,
         "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
@@ -328,23 +407,39 @@ def main():
                    "parallelism": f"clip-dp{world}", "color_correction": args.color_correction,
                    "source_resolution": [H // div, W // div], "l2": "inputs/activations per step (>10 GB) exceed L2; no flush needed",
                    "weights": "random init, reference key layout, fp16 checkpoint -> bf16 compute",
-                   "model_flops_per_clip": fm["dit"] + fm["enc"] + fm["dec"]},
+                   "model_flops_per_clip": model_flops, "peak_device_memory_gib": round(peak_mem / 2**30, 1)},
+        "dit_step_ms": dit_step_ms,
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frames_host.numel() * 2,
                 "d2h_bytes_per_step": out_host.numel() * 2,
                 "launch_mode": graph_note,
-                "note": "SeedVR2Engine.upscale_clip on pinned host frames at the source resolution (resized on the device); result copied back to host"},
+                "note": ("SeedVR2Engine.vae_decode on a pinned host latent; decoded frames copied back to host" if vae_only else
+                         "SeedVR2Engine.upscale_clip on pinned host frames at the source resolution (resized on the device); result copied back to host")},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (Linear + implicit-GEMM Conv3d + upsample)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "traffic": traffic, "traffic_detail": traffic_detail, "launches": g_calls, "kernel_ms_per_step": g_ms / args.steps,
-                     "share_of_step": g_ms / ms, "peak_source": peak_src},
+                     "share_of_step": g_ms / ms, "peak_source": peak_src,
+                     "note": "achieved = algorithmic FLOPs only (a duplicated QK^T pass of the VAE attention counts as time, not work)"},
+        "kernels": kernel_table(prof, args.steps, peak_tf, peak_gbs, ms / args.steps),
         "clocks": sampler.result(),
     }
+    if args.lib_baseline != "none" and not vae_only:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import gpu_library_baseline as glb
+            gl = {"ops": glb.op_level(dev)}
+            if args.lib_baseline in ("default", "full") and variant == "3b":
+                gl["phases_cfg2"] = glb.phase_level("cfg2", engine=eng, dev=dev)
+            if args.lib_baseline == "full" and variant == "3b":
+                gl["phases_4k_shard"] = glb.phase_level("4k_shard", engine=eng, dev=dev)
+            line["gpu_library_baseline"] = gl
+        except Exception as ex:   # noqa: BLE001 - a reported comparison must not cost the headline line
+            line["gpu_library_baseline"] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
     if not args.no_cpu_baseline:
         info = cpu_oracle_sample(frames_pad, H, W)
-        line["cpu_baseline"] = {"value": frames_real / info["est_clip_seconds"], "unit": "frames/s",
-                                "cores": info["cores"], "kind": "port", "sample": info["sample"],
-                                "rates_gflops": info["rates_gflops"]}
+        line["cpu_baseline"] = {"value": float(f"{frames_real / info['est_clip_seconds']:.2g}"), "unit": "frames/s",
+                                "cores": info["cores"], "kind": "port", "extrapolated": True, "sample": info["sample"],
+                                "rates_gflops": {k: round(v, 0) for k, v in info["rates_gflops"].items()}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

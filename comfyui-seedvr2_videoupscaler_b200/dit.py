@@ -221,7 +221,16 @@ class B200NaDiT:
                     W[f"{i}.{s}.mlp_in.b"] = self._w(sd, p + f"mlp.{key}.proj_in.bias")
                     W[f"{i}.{s}.mlp_out.w"] = self._w(sd, p + f"mlp.{key}.proj_out.weight")
                     W[f"{i}.{s}.mlp_out.b"] = self._w(sd, p + f"mlp.{key}.proj_out.bias")
-            self.rope_freqs.append(sd[p + "attn.rope.rope.freqs"].detach().cpu())
+            fr = sd.get(p + "attn.rope.rope.freqs")
+            if fr is None:
+                # the reference zero-fills persistent buffers a checkpoint does not carry (initialize_meta_buffers_impl,
+                # model_loader.py:777-815): zero frequencies = identity rotation — reproduce that
+                import warnings
+                warnings.warn(f"{p}attn.rope.rope.freqs missing from the checkpoint: zero-filled like the reference "
+                              "(RoPE becomes the identity)")
+                nfreq = (128 // 2 // 3) // 2 if cfg["variant"] == "7b" else (128 // 3) // 2
+                fr = torch.zeros(nfreq, dtype=sd["vid_in.proj.weight"].dtype)
+            self.rope_freqs.append(fr.detach().cpu())
         self.W = W
         # ---- time embedding (constant: t == 1000) and AdaSingle vectors
         half = 128
@@ -326,7 +335,7 @@ class B200NaDiT:
             lib.call("svr2_qk_norm_rope_window_bf16", lib.ptr(qkv_v), lib.ptr(qkv_t), lib.ptr(lay.row_src),
                      lib.ptr(lay.row_rope), lib.ptr(cos_t), lib.ptr(sin_t), nfreq, lib.ptr(k("vid", "nq")),
                      lib.ptr(k("vid", "nk")), lib.ptr(k("txt", "nq")), lib.ptr(k("txt", "nk")), cfg["eps"],
-                     lay.total, heads, lib.ptr(q), lib.ptr(kk), lib.ptr(v), st)
+                     lay.total, heads, lib.ptr(q), lib.ptr(kk), lib.ptr(v), st, nbytes=12.0 * lay.total * inner)
             del qkv_v
             o_view = o_all.view(-1, heads, 128)
             lib.attn_varlen(q, kk, v, lay.cu_seqlens, lay.max_len, out=o_view, out_row_map=lay.out_row_map,

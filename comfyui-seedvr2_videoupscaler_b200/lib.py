@@ -163,7 +163,8 @@ def _bf16c(t, name):
     return t
 
 
-def linear(a, w, *, bias=None, gate=None, residual=None, epi=0, out=None, out_scale=1.0, n_valid=None):
+def linear(a, w, *, bias=None, gate=None, residual=None, epi=0, out=None, out_scale=1.0, n_valid=None,
+           count_flops=True):
     """out = epi(a @ w^T).  a [M,K] (row stride lda), w [N,K]."""
     _bf16c(a, "a"), _bf16c(w, "w")
     M, K = a.shape
@@ -185,7 +186,7 @@ def linear(a, w, *, bias=None, gate=None, residual=None, epi=0, out=None, out_sc
     ldc = out.stride(0) // 2 if epi & EPI_ROWSTAT else out.stride(0)   # ROWSTAT: float2 slots per row
     call("svr2_linear_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epi, ptr(bias), ptr(gate),
          ptr(residual), ptr(out), ldc, float(out_scale), stream(),
-         flops=2.0 * M * (n_valid if n_valid is not None else N) * K,
+         flops=2.0 * M * (n_valid if n_valid is not None else N) * K if count_flops else 0.0,
          tag=f"|{M}x{N}x{K}|e{epi}" if (PROFILER is not None and PROFILER.detail) else "")
     return out
 

@@ -240,10 +240,15 @@ class GraphedClip:
         with torch.cuda.graph(self.graph):
             self.static_out = engine.upscale_clip(self.static_in, noise=self.noise, **clip_kwargs)
 
-    def __call__(self, frames: torch.Tensor) -> torch.Tensor:
+    def __call__(self, frames: torch.Tensor, clone: bool = False) -> torch.Tensor:
+        """Replay on new frames of the captured shape.  The returned tensor is the graph's STATIC output buffer: the
+        next replay overwrites it — pass ``clone=True`` (or copy it out, as bench.py does into pinned host memory)
+        when results of several clips are kept."""
+        if tuple(frames.shape) != tuple(self.static_in.shape):
+            raise ValueError(f"GraphedClip captured frames of shape {tuple(self.static_in.shape)}, got {tuple(frames.shape)}")
         self.static_in.copy_(frames, non_blocking=True)
         self.graph.replay()
-        return self.static_out
+        return self.static_out.clone() if clone else self.static_out
 
 
 def build_synthetic_engine(variant="3b", device="cuda", seed=1234, txt_len=58) -> SeedVR2Engine:

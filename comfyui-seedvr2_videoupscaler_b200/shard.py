@@ -95,13 +95,16 @@ def blend_overlap(prev_tail: torch.Tensor, cur_head: torch.Tensor) -> torch.Tens
     w_prev, w_cur = blend_weights(n, dt)
     wp, wc = w_prev.float().to(a.device), w_cur.float().to(a.device)
     elems = a[0].numel()
-    if elems % 8:
-        raise ValueError("frames must hold a multiple of 8 values")
+    shape = a.shape
+    pad = (-elems) % (4 if dt == torch.float32 else 8)     # the kernels move 16 bytes per thread
+    if pad:      # odd frame sizes (e.g. a max_resolution cap that rounds to odd H and W): pad each frame's tail
+        a = torch.nn.functional.pad(a.reshape(n, elems), (0, pad))
+        b = torch.nn.functional.pad(b.reshape(n, elems), (0, pad))
     out = torch.empty_like(a)
     name = "svr2_blend_overlap_f32" if dt == torch.float32 else "svr2_blend_overlap_bf16"
-    lib.call(name, lib.ptr(a), lib.ptr(b), lib.ptr(out), lib.ptr(wp), lib.ptr(wc), n, elems, lib.stream(),
+    lib.call(name, lib.ptr(a), lib.ptr(b), lib.ptr(out), lib.ptr(wp), lib.ptr(wc), n, elems + pad, lib.stream(),
              nbytes=3.0 * a.numel() * a.element_size())
-    return out
+    return out[:, :elems].reshape(shape) if pad else out
 
 
 def merge_shards(chunks: List[torch.Tensor], overlap: int, blend=None) -> torch.Tensor:

@@ -65,7 +65,6 @@ class B200VideoVAE:
         self.device = torch.device(device)
         self.W: Dict[str, torch.Tensor] = {}
         self._load(state_dict)
-        self._stats = None
         self._chunk = None          # {"first": bool, "state": {layer key: last two frames}} while slicing
         self.split_size = None      # explicit temporal slice length in sample frames (set_causal_slicing)
 
@@ -151,12 +150,13 @@ class B200VideoVAE:
                      nbytes=4.0 * x.T * x.H * x.W * x.C)
             self._halo(y, prefix)
             return y
+        # per-call scratch (a few hundred KB): engine-level scratch would be baked into a captured CUDA graph by address
+        # and could be rebound by a later, larger eager clip while the graph still writes to the old block
         need = lib.load().svr2_groupnorm_scratch_bytes(x.T, x.H * x.W, x.C)
-        if self._stats is None or self._stats.numel() * 8 < need:
-            self._stats = torch.empty((need + 7) // 8 + 1024, device=self.device, dtype=torch.float64)
+        stats = torch.empty((need + 7) // 8, device=self.device, dtype=torch.float64)
         lib.call("svr2_groupnorm_bf16", c_void_p(x.body_ptr()), lib.ptr(y.buf), x.T, x.H * x.W, x.C,
                  lib.ptr(self.W[prefix + ".weight"]), lib.ptr(self.W[prefix + ".bias"]), 1e-6, int(silu), pad,
-                 int(pad > 0 and self._first), lib.ptr(self._stats), self._stats.numel() * 8, lib.stream(),
+                 int(pad > 0 and self._first), lib.ptr(stats), stats.numel() * 8, lib.stream(),
                  nbytes=6.0 * x.T * x.H * x.W * x.C)
         self._halo(y, prefix)
         return y
@@ -254,7 +254,8 @@ class B200VideoVAE:
             lib.call("svr2_transpose_bf16", lib.ptr(vf), C, lib.ptr(vt), ldn, n, C, lib.stream())
             for r0 in range(0, n, cq):
                 rows = min(cq, n - r0)
-                lib.linear(qf[r0:r0 + rows], kf, epi=lib.EPI_ROWSTAT, out=part[:rows], out_scale=scale2)
+                lib.linear(qf[r0:r0 + rows], kf, epi=lib.EPI_ROWSTAT, out=part[:rows], out_scale=scale2,
+                           count_flops=False)     # the duplicated Q K^T pass is time, not algorithmic work
                 lib.call("svr2_rowstat_combine", lib.ptr(part), slots, slots, lib.ptr(lse), rows, lib.stream())
                 lib.linear(qf[r0:r0 + rows], k_buf[f * n: f * n + ldn], epi=lib.EPI_PEXP, gate=lse, out=P[:rows],
                            out_scale=scale2)

@@ -200,7 +200,7 @@ def time_embedding(sd, fl: _Flow, t: float) -> torch.Tensor:
     half = 128
     f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
     a = torch.tensor([t], dtype=torch.float32)[:, None] * f[None]
-    e = torch.cat([a.sin(), a.cos()], -1)
+    e = torch.cat([a.sin(), a.cos()], -1).to(sd["emb_in.proj_in.weight"].device)
     e = fl.act(e)
     e = fl.lin(e, sd["emb_in.proj_in.weight"], sd["emb_in.proj_in.bias"])
     e = F.silu(e)
@@ -235,12 +235,22 @@ def modulation_vectors(sd, cfg, emb: torch.Tensor) -> Dict[str, torch.Tensor]:
     return out
 
 
-def varlen_attention(q, k, v, lens: List[int], bf: bool) -> torch.Tensor:
-    """dit_3b/attention.py:27-64: per-sequence SDPA, non-causal, scale 1/sqrt(d)."""
+def varlen_attention(q, k, v, lens: List[int], bf: bool, impl: str = "math") -> torch.Tensor:
+    """dit_3b/attention.py:27-64: per-sequence SDPA, non-causal, scale 1/sqrt(d).
+    ``impl`` (ref_bf16 flow on a GPU only): "math" = explicit fp32 scores, bf16 probabilities (the rounding flow of a
+    fused kernel, runs anywhere); "sdpa" = torch's own fused bf16 SDPA per window, the reference's default backend
+    (attention.py:52-60); "flash_attn" = flash_attn_varlen_func (compatibility.py:321-330).  The latter two give the
+    reference-vs-reference noise floor."""
+    if bf and impl == "flash_attn":
+        from flash_attn import flash_attn_varlen_func
+        cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=q.device)
+        return flash_attn_varlen_func(q, k, v, cu, cu, max(lens), max(lens))
     outs, o = [], 0
     for n in lens:
         qi, ki, vi = (x[o:o + n].permute(1, 0, 2).unsqueeze(0) for x in (q, k, v))
-        if bf:
+        if bf and impl == "sdpa":
+            oi = F.scaled_dot_product_attention(qi, ki, vi)
+        elif bf:
             # fused kernels: fp32 scores/softmax, probabilities rounded to bf16 for P·V
             s = (qi.float() @ ki.float().transpose(-1, -2)) / math.sqrt(q.shape[-1])
             p = torch.softmax(s, -1)
@@ -258,12 +268,14 @@ def varlen_attention(q, k, v, lens: List[int], bf: bool) -> torch.Tensor:
 @torch.no_grad()
 def dit_forward(sd: Dict[str, torch.Tensor], cfg: dict, vid: torch.Tensor, txt: torch.Tensor,
                 T: int, H: int, W: int, timestep: float = 1000.0, mode: str = "fp32",
-                taps: dict | None = None) -> torch.Tensor:
+                taps: dict | None = None, attn_impl: str = "math") -> torch.Tensor:
     """NaDiT.forward (dit_3b/nadit.py:190-248, dit_7b/nadit.py:152-190), b = 1.
 
     vid (T*H*W, 33) latent-pixel rows; txt (l, 5120).  Returns vid_sample (T*H*W, 16).
     """
     fl = _Flow(mode)
+    dev = vid.device     # weights and inputs may live on a GPU (parity tests at benchmark sizes); index/RoPE tables are
+    #                      built on the host exactly as before and moved over
     d, nh, hd, eps = cfg["dim"], cfg["heads"], cfg["head_dim"], cfg["eps"]
     is7 = cfg["variant"] == "7b"
     vid, txt = fl.act(vid), fl.act(txt)
@@ -285,7 +297,8 @@ def dit_forward(sd: Dict[str, torch.Tensor], cfg: dict, vid: torch.Tensor, txt: 
     for shifted in (False, True):
         boxes = window_boxes(T, Hp, Wp, shifted)
         tgt, lens, loc = window_token_index(T, Hp, Wp, boxes)
-        layouts.append((tgt, lens.tolist(), loc, torch.argsort(tgt)))
+        layouts.append((tgt.to(dev), lens.tolist(), loc, torch.argsort(tgt).to(dev)))
+    rope_cache: Dict[tuple, tuple] = {}
 
     for i in range(cfg["layers"]):
         shared = i >= cfg["mm_layers"]
@@ -309,13 +322,19 @@ def dit_forward(sd: Dict[str, torch.Tensor], cfg: dict, vid: torch.Tensor, txt: 
         k_v = rms(k_v, eps) * sd[pre + f"attn.norm_k.{kv}.weight"].float()
         q_t = rms(q_t, eps) * sd[pre + f"attn.norm_q.{kt}.weight"].float()
         k_t = rms(k_t, eps) * sd[pre + f"attn.norm_k.{kt}.weight"].float()
-        freqs = sd[pre + "attn.rope.rope.freqs"]
+        freqs = sd[pre + "attn.rope.rope.freqs"].cpu()
+        rk = (i % 2, freqs.dtype, tuple(freqs.tolist()))                             # same table for every layer that
+        if rk not in rope_cache:                                                     # shares layout and frequencies
+            if not is7:
+                rope_cache[rk] = tuple(t.to(dev) for pair in rope_cos_sin_3b(freqs, loc, l) for t in pair)  # rope.py:130-176
+            else:
+                rope_cache[rk] = tuple(t.to(dev) for t in rope_cos_sin_7b(freqs, loc))
         if not is7:
-            (cv, sv), (ct, st) = rope_cos_sin_3b(freqs, loc, l)                      # rope.py:130-176
+            cv, sv, ct, st = rope_cache[rk]
             q_v, k_v = apply_rope(q_v, cv, sv), apply_rope(k_v, cv, sv)
             q_t, k_t = apply_rope(q_t, ct, st), apply_rope(k_t, ct, st)
         else:
-            cv, sv = rope_cos_sin_7b(freqs, loc)
+            cv, sv = rope_cache[rk]
             q_v, k_v = apply_rope(q_v, cv, sv), apply_rope(k_v, cv, sv)
         # concat text after every window (na.py:320-424) and run varlen attention
         qs, ks, vs, o = [], [], [], 0
@@ -325,7 +344,7 @@ def dit_forward(sd: Dict[str, torch.Tensor], cfg: dict, vid: torch.Tensor, txt: 
             vs += [v_v[o:o + n].float(), v_t.float()]
             o += n
         q_all, k_all, v_all = (fl.act(torch.cat(z)) for z in (qs, ks, vs))           # attention.py:118-121
-        out = varlen_attention(q_all, k_all, v_all, [n + l for n in lens], fl.bf).float()  # mmattn.py:257
+        out = varlen_attention(q_all, k_all, v_all, [n + l for n in lens], fl.bf, attn_impl).float()  # mmattn.py:257
         ov, ot, o = [], [], 0
         for n in lens:
             ov.append(out[o:o + n])

@@ -10,6 +10,23 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the fp32 oracle is the numerical ground truth: no TF32 in its convolutions / matmuls when it runs on the GPU
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def parity_record(name: str, **values):
+    """Append measured parity numbers to gpurun_out/parity_r2.json (copied to profiles/ by hand after a GPU run)."""
+    import json
+    path = os.path.join(ROOT, "gpurun_out", "parity_r2.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[name] = {k: (round(v, 3) if isinstance(v, float) else v) for k, v in values.items()}
+        json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
 
 
 @pytest.fixture(scope="session")

@@ -199,6 +199,12 @@ def test_blend_overlap_vs_reference_golden(pkg):
     a = torch.rand(3, 270, 480, 3, generator=g).to(torch.bfloat16)
     b = torch.rand(3, 270, 480, 3, generator=g).to(torch.bfloat16)
     assert torch.equal(shard.blend_overlap(a.cuda(), b.cuda()).float().cpu(), color_oracle.blend_overlapping_frames(a, b, 3))
+    # odd frame sizes (3 * 7 * 9 = 189 values per frame: neither % 8 nor % 4), both dtypes — the reference blends any size
+    for dt in (torch.bfloat16, torch.float32):
+        a = torch.rand(2, 7, 9, 3, generator=g).to(dt)
+        b = torch.rand(2, 7, 9, 3, generator=g).to(dt)
+        out = shard.blend_overlap(a.cuda(), b.cuda())
+        assert out.shape == a.shape and torch.equal(out.cpu(), color_oracle.blend_overlapping_frames(a, b, 2).to(dt)), dt
 
 
 def test_merge_shards_fp32_kernel(pkg):
