@@ -190,7 +190,13 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int quad = warp & 3;                 // TMEM lane quadrant accessible to this warp
     const int row = quad * 32 + lane;          // query row within the tile
     const uint32_t lane_off = uint32_t(quad * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
+    // m_ref is the row maximum the exponentials are taken against.  It only moves when the running maximum has grown
+    // by more than 2^kGrow since (FA4's thresholded rescale): P then holds values up to 2^kGrow instead of <= 1 — exact
+    // in fp32 / bf16 (relative rounding), and the O rescale below (four TMEM round trips on the critical path) becomes
+    // rare instead of happening on almost every early tile.
+    constexpr float kGrow = 8.0f;
+    float m_ref = -INFINITY, l_run = 0.f;
+    const float sc = p.scale_log2;
     uint8_t* sp = smem + AttnSmem::kP;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
@@ -201,39 +207,53 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(s_free);                      // S may be overwritten by the next QK^T
-      const int kv_valid = len - j * ATT_BN;    // columns >= kv_valid are padding / next sequence
-      float mx = m_run;
+      const int kv_valid = len - j * ATT_BN;    // columns >= kv_valid are padding / the next sequence
+      if (kv_valid < ATT_BN) {                  // only the last tile of a sequence is ragged
 #pragma unroll
-      for (int c = 0; c < ATT_BN; ++c) {
-        float s = __uint_as_float(sv[c]);
-        s = (c < kv_valid) ? s : -INFINITY;
-        sv[c] = __float_as_uint(s);
-        mx = fmaxf(mx, s);
+        for (int c = 0; c < ATT_BN; ++c)
+          if (c >= kv_valid) sv[c] = 0xff800000u;   // -inf
       }
-      const float alpha = fast_exp2((m_run - mx) * p.scale_log2);   // 0 on the first tile (m_run = -inf)
-      const float mb = mx * p.scale_log2;
-      float lsum = 0.f;
-      // P values first (independent of the previous P·V), then wait for it before touching O / the P buffer
+      // row maximum: four independent chains of 3-input max
+      float mx4[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) mx4[a] = __uint_as_float(sv[a]);
+#pragma unroll
+      for (int c = 4; c < ATT_BN; c += 8) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          mx4[a] = fmaxf(fmaxf(mx4[a], __uint_as_float(sv[c + a])), __uint_as_float(sv[(c + 4 + a) & (ATT_BN - 1)]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const bool grow = (mx - m_ref) * sc > kGrow;                   // true on the first tile (m_ref = -inf)
+      const float m_new = grow ? mx : m_ref;
+      const float alpha = grow ? fast_exp2((m_ref - m_new) * sc) : 1.0f;   // 0 on the first tile
+      const float2 nmb = make_float2(-m_new * sc, -m_new * sc);
+      const float2 sc2 = make_float2(sc, sc);
+      // P = exp2(s * sc - m_new * sc): packed fp32x2 FMAs, four independent partial sums
+      float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       uint32_t pk[ATT_BN / 2];
 #pragma unroll
       for (int c = 0; c < ATT_BN; c += 2) {
-        const float p0 = fast_exp2(__uint_as_float(sv[c]) * p.scale_log2 - mb);
-        const float p1 = fast_exp2(__uint_as_float(sv[c + 1]) * p.scale_log2 - mb);
-        lsum += p0 + p1;
-        pk[c / 2] = pack_bf16x2(p0, p1);
+        const float2 t = ffma2(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sc2, nmb);
+        const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+        ls[(c >> 1) & 1] = fadd2(ls[(c >> 1) & 1], e);
+        pk[c / 2] = pack_bf16x2(e.x, e.y);
       }
+      const float lsum = (ls[0].x + ls[1].x) + (ls[0].y + ls[1].y);
       if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);
+        mbar_wait(pv_done, (j - 1) & 1);        // P_{j-1} V_{j-1} has read the P buffer and updated O
         tc_fence_after();
-        if (!__all_sync(0xffffffffu, alpha == 1.0f)) {
+        if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            uint32_t o[32];
-            tmem_ld32(tmem_o + lane_off + c0, o);
+          for (int c0 = 0; c0 < 128; c0 += 64) {
+            uint32_t o[64];
+            tmem_ld32(tmem_o + lane_off + c0, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+            tmem_ld32(tmem_o + lane_off + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
             tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-            tmem_st32(tmem_o + lane_off + c0, o);
+            for (int e = 0; e < 64; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st32(tmem_o + lane_off + c0, *reinterpret_cast<const uint32_t(*)[32]>(&o[0]));
+            tmem_st32(tmem_o + lane_off + c0 + 32, *reinterpret_cast<const uint32_t(*)[32]>(&o[32]));
           }
           tmem_st_wait();
         }
@@ -245,7 +265,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
       }
       l_run = l_run * alpha + lsum;
-      m_run = mx;
+      m_ref = m_new;
       fence_proxy_async_smem();                  // make P visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_ready);
@@ -293,12 +313,13 @@ extern "C" int svr2_attn_varlen_bf16(const void* q, const void* k, const void* v
                                      const int32_t* out_row_map, void* stream) {
   if (n_seq <= 0 || total <= 0) return SVR2_OK;
   if (max_seqlen <= 0) return set_error(SVR2_ERR_ARG, "svr2_attn_varlen_bf16: max_seqlen must be > 0");
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};                // the attribute is per (function, device)
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(attn_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          AttnSmem::kTotal);
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
-    configured = true;
+    configured[dev] = true;
   }
   CUtensorMap tq, tk, tv;
   uint64_t dims[2] = {(uint64_t)heads * ATT_D, (uint64_t)total};

@@ -48,6 +48,8 @@ struct GemmParams {
   int taps_t, taps_h, taps_w;
   int cin_blocks;        // Cin / 64
   int cin;               // Cin (pair view channel offset)
+  int extra_blocks;      // conv: trailing 64-channel k-blocks read from the SECOND activation tensor (tmap_a2) at the
+                         // output pixel itself (a fused 1x1x1 conv_shortcut: [h ; x] . [W2 ; Wsc], attn_video_vae.py:311-362)
   int pad_h, pad_w;      // subtracted from the tap offset (1 for padding=1)
   int stride_t;          // temporal stride of the conv (1 or 2)
   int H_out, W_out, T_out;
@@ -200,7 +202,7 @@ __device__ __forceinline__ RowDest row_dest(const GemmParams& p, int m_blk, int 
 template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_a2, const GemmParams p) {
   static_assert(!(SWAP && TWO), "swap-AB and CTA pairs are mutually exclusive");
   using L = SmemLayout<BLOCK_N, TWO>;
   const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
@@ -222,6 +224,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.extra_blocks) tma_prefetch_desc(&tmap_a2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -345,6 +348,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
               }
             }
+          }
+          // fused 1x1x1 shortcut: extra k-blocks from the second tensor at the output pixels (no tap offset, no halo)
+          for (int cb = 0; cb < p.extra_blocks; ++cb) {
+            uint8_t* sa; uint64_t* fb;
+            if (acquire(sa, fb)) {
+              uint8_t* s_act = SWAP ? sa + L::kABytes : sa;
+              uint8_t* s_wgt = SWAP ? sa : sa + L::kABytes;
+              if constexpr (TWO) {
+                tma2_load_4d(s_act, &tmap_a2, fb, cb * BLOCK_K, w0, h0, t_o);
+                tma2_load_2d(s_wgt, &tmap_b, fb, kcol, n0);
+              } else {
+                tma_load_4d(s_act, &tmap_a2, fb, cb * BLOCK_K, w0, h0, t_o);
+                tma_load_2d(s_wgt, &tmap_b, fb, kcol, n0);
+              }
+            }
+            kcol += BLOCK_K;
+            advance();
           }
         }
       }
@@ -872,18 +892,24 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   return SVR2_OK;
 }
 
-static int g_num_sms = 0;
+// per-device caches: a host process may drive several GPUs (ComfyUI), so nothing here is cached per process
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+static int g_num_sms[kMaxDevices] = {};
 int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return g_num_sms;
+  const int dev = current_device();
+  if (!g_num_sms[dev]) cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return g_num_sms[dev];
 }
 
 template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, cudaStream_t stream,
+                       const CUtensorMap* ta2_opt = nullptr) {
+  const CUtensorMap& ta2 = ta2_opt ? *ta2_opt : ta;
   using L = SmemLayout<BLOCK_N, TWO>;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, KIND, SWAP, TWO>;
   GemmParams p = p_in;
@@ -895,11 +921,12 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     if (g > p.num_n_tiles) g = p.num_n_tiles;
     p.group_n = (int)g;
   }
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};       // the attribute is per (function, device)
+  const int dev = current_device();
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
-    configured = true;
+    configured[dev] = true;
   }
   if constexpr (TWO) {
     const int tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
@@ -918,14 +945,14 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ta2, p);
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
     return SVR2_OK;
   } else {
     int tiles = p.num_m_tiles * p.num_n_tiles;
     int grid = tiles < num_sms() ? tiles : num_sms();
     if (grid <= 0) return SVR2_OK;
-    kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
+    kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, ta2, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
     return SVR2_OK;
@@ -951,7 +978,15 @@ static bool want_pair(int block_n, int epi, int num_m_tiles) {
 }
 
 static int dispatch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                         cudaStream_t s, bool pair = false) {
+                         cudaStream_t s, bool pair = false, const CUtensorMap* ta2 = nullptr) {
+  if (ta2) {     // conv with a fused shortcut: plain bf16 epilogue only
+    if (pair) return launch_gemm<256, KIND_BF16, false, true>(ta, tb, p, s, ta2);
+    switch (block_n) {
+      case 256: return launch_gemm<256, KIND_BF16>(ta, tb, p, s, ta2);
+      case 128: return launch_gemm<128, KIND_BF16>(ta, tb, p, s, ta2);
+    }
+    return set_error(SVR2_ERR_ARG, "fused shortcut: Cout must be >= 128");
+  }
   if (pair) {
     if (p.epi & EPI_SWIGLU) return launch_gemm<256, KIND_SWIGLU, false, true>(ta, tb, p, s);
     if (p.epi & EPI_ROWSTAT) return launch_gemm<256, KIND_ROWSTAT, false, true>(ta, tb, p, s);
@@ -1070,7 +1105,8 @@ extern "C" int svr2_rowstat_slots(int N) {
 static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout, int kt,
                        int kh, int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags,
                        const void* bias, const void* residual, void* y, int out_t_pad, int out_dup_head,
-                       int ldc, void* stat_partial, int64_t stat_bytes, int* stat_slots_out, void* stream);
+                       int ldc, void* stat_partial, int64_t stat_bytes, int* stat_slots_out, void* stream,
+                       const void* x2 = nullptr, int C2 = 0);
 
 extern "C" int svr2_conv3d_bf16(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout, int kt,
                                 int kh, int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags,
@@ -1093,10 +1129,24 @@ extern "C" int svr2_conv3d_stats_bf16(const void* x, int T_in_total, int H, int 
                      residual, y, out_t_pad, out_dup_head, ldc, stat_partial, stat_bytes, stat_slots, stream);
 }
 
+// Same conv with a fused 1x1x1 conv_shortcut (ResnetBlock3D, attn_video_vae.py:311-362): y = conv(x; w[:, :K]) +
+// x2 . w[:, K:]^T + bias, x2 = [T_out, H, W, C2] (no halo), w = [Cout][kt*kh*kw*Cin + C2], bias = conv bias + shortcut
+// bias.  One fp32 accumulation, one rounding (the reference rounds the shortcut and the conv output separately).
+extern "C" int svr2_conv3d_shortcut_stats_bf16(const void* x, int T_in_total, int H, int W, int Cin, const void* w,
+                                               int Cout, int kt, int kh, int kw, int T_out, const void* bias,
+                                               const void* x2, int C2, void* y, int out_t_pad, int out_dup_head,
+                                               void* stat_partial, int64_t stat_bytes, int* stat_slots, void* stream) {
+  if (!x2 || C2 <= 0 || (C2 % 64)) return set_error(SVR2_ERR_ARG, "svr2_conv3d_shortcut_stats_bf16: x2 / C2 % 64");
+  if (Cout < 128) return set_error(SVR2_ERR_ARG, "svr2_conv3d_shortcut_stats_bf16: Cout must be >= 128");
+  return conv3d_impl(x, T_in_total, H, W, Cin, w, Cout, kt, kh, kw, 1, 1, 1, T_out, EPI_BIAS, bias, nullptr, y,
+                     out_t_pad, out_dup_head, Cout, stat_partial, stat_bytes, stat_slots, stream, x2, C2);
+}
+
 static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout, int kt,
                        int kh, int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags,
                        const void* bias, const void* residual, void* y, int out_t_pad, int out_dup_head,
-                       int ldc, void* stat_partial, int64_t stat_bytes, int* stat_slots_out, void* stream) {
+                       int ldc, void* stat_partial, int64_t stat_bytes, int* stat_slots_out, void* stream,
+                       const void* x2, int C2) {
   if (Cin % 64) return set_error(SVR2_ERR_ARG, "svr2_conv3d_bf16: Cin must be a multiple of 64 (pad channels)");
   if (Cout % 8 || ldc % 8) return set_error(SVR2_ERR_ARG, "svr2_conv3d_bf16: Cout/ldc must be multiples of 8");
   if (stride_hw != 1 && stride_hw != 2) return set_error(SVR2_ERR_ARG, "stride_hw must be 1 or 2");
@@ -1129,7 +1179,15 @@ static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, con
     rc = make_tmap_bf16(&ta, x, 5, d, s, b);
   }
   if (rc) return rc;
-  const int K = kt * kh * kw * Cin;
+  CUtensorMap ta2;
+  if (x2) {   // second activation tensor: same pixel box, read at the output pixel
+    uint64_t d[4] = {(uint64_t)C2, (uint64_t)W, (uint64_t)H, (uint64_t)T_out};
+    uint64_t s2[3] = {(uint64_t)C2 * 2, (uint64_t)W * C2 * 2, (uint64_t)H * W * C2 * 2};
+    uint32_t b[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, 1};
+    rc = make_tmap_bf16(&ta2, x2, 4, d, s2, b);
+    if (rc) return rc;
+  }
+  const int K = kt * kh * kw * Cin + (x2 ? C2 : 0);
   const int n_m_tiles = T_out * ((W_out + bw - 1) / bw) * ((H_out + bh - 1) / bh);
   const bool pair = !swap && want_pair(bn, 0, n_m_tiles);
   uint64_t db[2] = {(uint64_t)K, (uint64_t)Cout}, sb[1] = {(uint64_t)K * 2};
@@ -1143,6 +1201,7 @@ static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, con
   p.tiles_h = (H_out + bh - 1) / bh;
   p.taps_t = kt; p.taps_h = kh; p.taps_w = kw;
   p.cin_blocks = Cin / 64; p.cin = Cin;
+  p.extra_blocks = x2 ? C2 / 64 : 0;
   p.pad_h = p.pad_w = pad_hw;
   p.stride_t = stride_t;
   p.H_out = H_out; p.W_out = W_out; p.T_out = T_out;
@@ -1177,8 +1236,8 @@ static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, con
     p.stat_partial = (float4*)stat_partial;
     p.stat_slots = slots;
   }
-  if (swap) return launch_gemm<256, KIND_BF16, true>(ta, tb, p, (cudaStream_t)stream);
-  return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream, pair);
+  if (swap) return launch_gemm<256, KIND_BF16, true>(ta, tb, p, (cudaStream_t)stream, x2 ? &ta2 : nullptr);
+  return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream, pair, x2 ? &ta2 : nullptr);
 }
 
 // Upsample3D: 1x1x1 conv (GEMM over voxels) with the 3-D pixel shuffle fused into the store.

@@ -9,7 +9,8 @@
 
 namespace svr2 {
 int set_error(int code, const char* msg);  // records the message for svr2_last_error(), returns code
-int num_sms();
+int num_sms();          // of the current device
+int current_device();   // cudaGetDevice, clamped to the per-device cache size
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
 inline int check_launch(const char* what) {

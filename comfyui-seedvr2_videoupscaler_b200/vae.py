@@ -21,6 +21,7 @@ at the same layer (the reference's ``InflatedCausalConv3d.memory``,
 """
 from __future__ import annotations
 
+import os
 from ctypes import c_void_p
 from typing import Dict, Optional
 
@@ -116,6 +117,16 @@ class B200VideoVAE:
             if k.endswith(".weight") and v.ndim == 5:
                 W[k + ".k"] = tuple(v.shape[2:])
                 W[k + ".real"] = (v.shape[0], v.shape[1])   # un-padded (Cout, Cin) for the FLOP model
+
+        # ResnetBlock3D with a channel change: conv2 and the 1x1x1 conv_shortcut become ONE contraction
+        # [hidden ; x] . [W2 ; Wsc] (svr2_conv3d_shortcut_stats_bf16): concatenate the K-major weight rows, sum the biases
+        for k in [k for k in W if k.endswith("conv_shortcut.weight")]:
+            p = k[: -len("conv_shortcut.weight")]
+            wsc = W[k].reshape(W[k].shape[0], -1)                                   # [Cout, Cin] (1x1x1)
+            W[p + "conv2+shortcut.weight"] = torch.cat([W[p + "conv2.weight"], wsc], 1).contiguous()
+            W[p + "conv2+shortcut.bias"] = (W[p + "conv2.bias"].float() + W[p + "conv_shortcut.bias"].float()
+                                            ).to(torch.bfloat16).contiguous()
+        self.fuse_shortcut = os.environ.get("SVR2_FUSE_SHORTCUT", "1") != "0"      # 0: separate launch (A/B measurements)
 
     def parameters(self):
         return iter(v for v in self.W.values() if torch.is_tensor(v))
@@ -213,10 +224,35 @@ class B200VideoVAE:
         h = self._conv(h, p + "conv1", stats=True)
         h = self._gn(h, p + "norm2", True, 2)
         if (p + "conv_shortcut.weight") in self.W:
+            if self.fuse_shortcut:
+                return self._conv_shortcut(h, x, p, out_pad)
             sc = self._conv(x.without_halo(), p + "conv_shortcut")
         else:
             sc = x
         return self._conv(h, p + "conv2", out_pad=out_pad, residual=sc, stats=True)
+
+    def _conv_shortcut(self, h: Act, x: Act, p: str, out_pad: int) -> Act:
+        """conv2(h) + conv_shortcut(x) as one implicit GEMM over [h ; x] (see _load); statistics for the next GroupNorm."""
+        import ctypes
+        w, b = self.W[p + "conv2+shortcut.weight"], self.W[p + "conv2+shortcut.bias"]
+        kt, kh, kw = self.W[p + "conv2.weight.k"]
+        Cout, C2 = w.shape[0], x.C
+        assert h.pad == kt - 1 and (h.T, h.H, h.W) == (x.T, x.H, x.W) and h.C == Cout
+        y = Act(h.T, h.H, h.W, Cout, out_pad, self.device)
+        args = (lib.ptr(h.buf), h.pad + h.T, h.H, h.W, h.C, lib.ptr(w), Cout, kt, kh, kw, h.T, lib.ptr(b),
+                c_void_p(x.body_ptr()), C2, lib.ptr(y.buf), out_pad, int(out_pad > 0 and self._first))
+        slots = ctypes.c_int(0)
+        rc = lib.load().svr2_conv3d_shortcut_stats_bf16(*args, None, 0, ctypes.byref(slots), lib.stream())   # size query
+        if rc:
+            raise lib.Svr2Error(f"svr2_conv3d_shortcut_stats_bf16 query failed ({rc}): {lib.load().svr2_last_error().decode()}")
+        part = torch.empty(h.T * slots.value * (Cout // 8) * 4, device=self.device, dtype=torch.float32)
+        y.stats = (part, slots.value)
+        lib.call("svr2_conv3d_shortcut_stats_bf16", *args, lib.ptr(part), part.numel() * 4, ctypes.byref(slots), lib.stream(),
+                 flops=2.0 * h.T * h.H * h.W * Cout * (kt * kh * kw * h.C + C2),
+                 tag=(f"|{h.C}+{C2}>{Cout}|k{kt}{kh}{kw}|s11|{h.T}x{h.H}x{h.W}"
+                      if (lib.PROFILER is not None and lib.PROFILER.detail) else ""))
+        self._halo(y, p + "conv2:out")
+        return y
 
     def _attention(self, x: Act, p: str) -> Act:
         """UNetMidBlock3D per-frame attention (attn_video_vae.py:656-668): GN -> q,k,v -> 1-head

@@ -72,6 +72,17 @@ int svr2_conv3d_stats_bf16(const void* x, int T_in_total, int H, int W, int Cin,
                            const void* residual, void* y, int out_t_pad, int out_dup_head, int ldc, void* stat_partial,
                            int64_t stat_bytes, int* stat_slots, void* stream);
 
+/* Stride-1 causal conv with the ResnetBlock3D 1x1x1 conv_shortcut fused in as extra K-blocks (attn_video_vae.py:311-362:
+ * `x = conv_shortcut(x); return x + hidden`): y = conv(x; w[:, :kt*kh*kw*Cin]) + x2 . w[:, kt*kh*kw*Cin:]^T + bias,
+ * x2 = [T_out, H, W, C2] bf16 (the block input, no halo, C2 % 64 == 0), w = [Cout][kt*kh*kw*Cin + C2] (conv2 weight rows
+ * followed by the shortcut weight rows), bias = conv bias + shortcut bias.  One fp32 accumulation and one bf16 rounding
+ * replace the reference's two roundings + add; saves the shortcut launch, its output write and the residual re-read.
+ * Statistics output as svr2_conv3d_stats_bf16 (stat_partial == NULL: size query). */
+int svr2_conv3d_shortcut_stats_bf16(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout, int kt,
+                                    int kh, int kw, int T_out, const void* bias, const void* x2, int C2, void* y,
+                                    int out_t_pad, int out_dup_head, void* stat_partial, int64_t stat_bytes,
+                                    int* stat_slots, void* stream);
+
 /* ---- Upsample3D: 1x1x1 conv + 'b (x y z c) f h w -> b c (f z) (h x) (w y)' + remove_head
  * (attn_video_vae.py:135-153, causal_inflation_lib.py:412-419) in one GEMM. */
 int svr2_upsample_shuffle_bf16(const void* x, int F, int H, int W, int C, const void* w, const void* bias,

@@ -144,6 +144,43 @@ def test_conv3d(svr2lib, Cin, Cout, k, st, shw, T, H, W):
     assert torch.equal(y[0], y[2]) and torch.equal(y[1], y[2]), "halo frames must replicate frame 0"
 
 
+@pytest.mark.parametrize("Cin,C2,Cout,T,H,W", [
+    (128, 256, 128, 2, 30, 44),     # decoder up3.res0: swap-AB, ragged tile edges
+    (256, 512, 256, 3, 24, 40),     # decoder up2.res0: CTA pair
+    (256, 128, 256, 2, 17, 33),     # encoder down1.res0 (odd sizes)
+    (512, 256, 512, 1, 9, 16),      # encoder down2.res0, single frame
+])
+def test_conv3d_fused_shortcut(svr2lib, Cin, C2, Cout, T, H, W):
+    """conv2(h) + conv_shortcut(x) as one contraction over [h ; x] (ResnetBlock3D, attn_video_vae.py:311-362) vs torch:
+    fp32 reference of the two convolutions on bf16-rounded operands; statistics slots returned."""
+    import ctypes
+    h = rnd(1, Cin, T, H, W, seed=1)
+    x2 = rnd(1, C2, T, H, W, seed=2)
+    w = rnd(Cout, Cin, 3, 3, 3, std=(27 * Cin) ** -0.5, seed=3)
+    wsc = rnd(Cout, C2, 1, 1, 1, std=C2 ** -0.5, seed=4)
+    b, bsc = rnd(Cout, seed=5), rnd(Cout, seed=6)
+    hb, xb = bf(h).float(), bf(x2).float()
+    hp = torch.cat([hb[:, :, :1]] * 2 + [hb], 2)
+    ref = F.conv3d(hp, bf(w).float(), None, padding=(0, 1, 1)) + F.conv3d(xb, bf(wsc).float(), None)
+    bsum = bf(bf(b).float() + bf(bsc).float())
+    ref = ref + bsum.float().view(1, -1, 1, 1, 1)
+    h_nd, x_nd = _to_ndhwc(h, 2), _to_ndhwc(x2, 0)
+    w_cat = torch.cat([bf(w.permute(0, 2, 3, 4, 1).reshape(Cout, -1)), bf(wsc.reshape(Cout, C2))], 1).contiguous()
+    y = torch.zeros(2 + T, H, W, Cout, device=DEV, dtype=torch.bfloat16)
+    args = (svr2lib.ptr(h_nd), T + 2, H, W, Cin, svr2lib.ptr(w_cat), Cout, 3, 3, 3, T, svr2lib.ptr(bsum),
+            svr2lib.ptr(x_nd), C2, svr2lib.ptr(y), 2, 1)
+    slots = ctypes.c_int(0)
+    assert svr2lib.load().svr2_conv3d_shortcut_stats_bf16(*args, None, 0, ctypes.byref(slots), svr2lib.stream()) == 0
+    part = torch.zeros(T * slots.value * (Cout // 8) * 4, device=DEV, dtype=torch.float32)
+    svr2lib.call("svr2_conv3d_shortcut_stats_bf16", *args, svr2lib.ptr(part), part.numel() * 4, ctypes.byref(slots),
+                 svr2lib.stream())
+    assert_close(y[2:], ref[0].permute(1, 2, 3, 0), 4e-3, "conv + fused shortcut")
+    assert torch.equal(y[0], y[2]) and torch.equal(y[1], y[2])
+    # the statistics the epilogue emitted: per-frame sums of the stored values
+    sums = part.view(T, slots.value, Cout // 8, 4)[..., [0, 2]].sum((1, 2, 3))
+    assert_close(sums, y[2:].float().sum((1, 2, 3)), 2e-3, "epilogue statistics (sum)")
+
+
 @pytest.mark.parametrize("C,temporal,F_,H,W", [(256, 0, 3, 6, 10), (512, 1, 3, 4, 6), (512, 1, 1, 4, 6),
                                                 # W % 32 == 0: the TMA shuffle-store path (incl. a ragged last m-tile)
                                                 (256, 0, 2, 5, 32), (512, 1, 3, 3, 64), (256, 1, 2, 7, 96)])
