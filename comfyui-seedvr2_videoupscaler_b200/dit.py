@@ -24,7 +24,9 @@ from typing import Dict, List, Tuple
 import torch
 
 from . import lib
+from .attention import FlashAttentionVarlen
 from .lib import EPI_GELU, EPI_SILU, EPI_SWIGLU
+from .module import EngineModule
 
 
 def dit_config(variant: str = "3b", **over) -> dict:
@@ -159,17 +161,25 @@ class NaDiTOutput:
         self.vid_sample = vid_sample
 
 
-class B200NaDiT:
-    """Drop-in for the reference ``runner.dit`` (VideoDiffusionInfer model slot, infer.py:361-367)."""
+class B200NaDiT(EngineModule):
+    """Drop-in for the reference ``runner.dit`` (VideoDiffusionInfer model slot, infer.py:361-367): an ``nn.Module``
+    whose weights are buffers in the kernels' layout (see ``module.EngineModule`` for the lifecycle it survives) and
+    which holds one ``FlashAttentionVarlen`` submodule, the class ``apply_model_specific_config`` looks for."""
 
     K_IN_PAD = 192  # 4*33 = 132 patch channels padded to 3 k-blocks of 64
 
     def __init__(self, cfg: dict, state_dict: Dict[str, torch.Tensor], device="cuda", timestep: float = 1000.0):
+        super().__init__(device)
         lib.device_check()
-        self.cfg, self.device = cfg, torch.device(device)
+        self.cfg = cfg
         self.timestep = timestep
         self._layouts: Dict[tuple, tuple] = {}
+        self.attention = FlashAttentionVarlen()
         self._load(state_dict)
+
+    def _device_state_moved(self):
+        if hasattr(self, "_layouts"):
+            self._layouts.clear()      # window / RoPE tables live on the old device
 
     # ---- weights ---------------------------------------------------------
     def _w(self, sd, key):
@@ -231,7 +241,7 @@ class B200NaDiT:
                 nfreq = (128 // 2 // 3) // 2 if cfg["variant"] == "7b" else (128 // 3) // 2
                 fr = torch.zeros(nfreq, dtype=sd["vid_in.proj.weight"].dtype)
             self.rope_freqs.append(fr.detach().cpu())
-        self.W = W
+        self.W = self._register("w", W)
         # ---- time embedding (constant: t == 1000) and AdaSingle vectors
         half = 128
         f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
@@ -240,7 +250,6 @@ class B200NaDiT:
         e = lib.linear(e, self._w(sd, "emb_in.proj_in.weight"), bias=self._w(sd, "emb_in.proj_in.bias"), epi=EPI_SILU)
         e = lib.linear(e, self._w(sd, "emb_in.proj_hid.weight"), bias=self._w(sd, "emb_in.proj_hid.bias"), epi=EPI_SILU)
         e = lib.linear(e, self._w(sd, "emb_in.proj_out.weight"), bias=self._w(sd, "emb_in.proj_out.bias"))
-        self.emb = e
         E = e.float().view(d, 2, 3)     # [channel, layer{attn,mlp}, {shift,scale,gate}]  modulation.py:76
         M: Dict[str, torch.Tensor] = {}
         ones, zeros = torch.ones(d, device=dev), torch.zeros(d, device=dev)
@@ -260,7 +269,8 @@ class B200NaDiT:
             M["out_shift"] = (E[:, 0, 0] + self._f(sd, "vid_out_ada.out_shift")).contiguous()
             M["out_scale"] = (E[:, 0, 1] + self._f(sd, "vid_out_ada.out_scale")).contiguous()
             M["out_weight"] = self._f(sd, "vid_out_norm.weight")
-        self.M = M
+        self.M = self._register("m", M)
+        self.emb = None          # the raw time embedding is folded into M
 
     # ---- geometry cache ----------------------------------------------------
     def _geometry(self, T, Hp, Wp, l):
@@ -288,6 +298,12 @@ class B200NaDiT:
     @torch.no_grad()
     def forward(self, vid, txt, vid_shape, txt_shape, timestep=None, disable_cache=False):
         """vid (T*H*W, 33), txt (l, 5120); vid_shape [[T,H,W]], txt_shape [[l]] (b = 1)."""
+        self._require_cuda("B200NaDiT.forward")
+        if timestep is not None:
+            t_in = float(torch.as_tensor(timestep).reshape(-1)[0])
+            if abs(t_in - self.timestep) > 1e-3:
+                raise lib.Svr2Error(f"B200NaDiT folds the time embedding of t = {self.timestep} into its AdaSingle vectors "
+                                    f"at load (one-step sampling, SURVEY.md fact 2); got t = {t_in}")
         cfg, W, M = self.cfg, self.W, self.M
         vs = vid_shape.tolist() if torch.is_tensor(vid_shape) else list(vid_shape)
         ts = txt_shape.tolist() if torch.is_tensor(txt_shape) else list(txt_shape)
@@ -338,8 +354,8 @@ class B200NaDiT:
                      lay.total, heads, lib.ptr(q), lib.ptr(kk), lib.ptr(v), st, nbytes=12.0 * lay.total * inner)
             del qkv_v
             o_view = o_all.view(-1, heads, 128)
-            lib.attn_varlen(q, kk, v, lay.cu_seqlens, lay.max_len, out=o_view, out_row_map=lay.out_row_map,
-                            flops=lay.attn_flops * heads)
+            self.attention.run(q, kk, v, lay.cu_seqlens, lay.max_len, out=o_view, out_row_map=lay.out_row_map,
+                               flops=lay.attn_flops * heads)
             lib.call("svr2_txt_window_mean_bf16", lib.ptr(o_all[L:]), lib.ptr(o_t), lay.n_win, l, inner, st)
             h_v = lib.linear(o_all[:L], k("vid", "out.w"), bias=k("vid", "out.b"), gate=m("vid.attn_gate"), residual=x)
             h_t = lib.linear(o_t, k("txt", "out.w"), bias=k("txt", "out.b"),
@@ -358,8 +374,6 @@ class B200NaDiT:
         lib.call("svr2_unpatchify_bf16", lib.ptr(v64), v64.stride(0), lib.ptr(out), T, H, Wd, cfg["out_ch"], st)
         return NaDiTOutput(out)
 
-    __call__ = forward
-
     def _mlp(self, i, s, h):
         cfg, W, M = self.cfg, self.W, self.M
         mm = lib.rmsnorm_ada(h, M[f"{i}.{s}.mlp_scale"], M[f"{i}.{s}.mlp_shift"], mode=1, eps=cfg["eps"])
@@ -370,9 +384,3 @@ class B200NaDiT:
         return lib.linear(z, W[f"{i}.{s}.mlp_out.w"], bias=W[f"{i}.{s}.mlp_out.b"], gate=M[f"{i}.{s}.mlp_gate"],
                           residual=h)
 
-    # ---- reference model-slot surface --------------------
-    def parameters(self):
-        return iter(self.W.values())
-
-    def to(self, *a, **k):
-        return self

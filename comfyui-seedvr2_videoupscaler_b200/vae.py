@@ -28,6 +28,7 @@ from typing import Dict, Optional
 import torch
 
 from . import lib
+from .module import EngineModule
 
 
 class Act:
@@ -58,16 +59,19 @@ class VAEOutput:
         self.__dict__.update(kw)
 
 
-class B200VideoVAE:
-    """Drop-in for the reference ``runner.vae`` (model-slot seam, infer.py:125-266)."""
+class B200VideoVAE(EngineModule):
+    """Drop-in for the reference ``runner.vae`` (model-slot seam, infer.py:125-266): an ``nn.Module`` with the weights
+    as buffers in the kernels' layout (``module.EngineModule``)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda"):
+        super().__init__(device)
         lib.device_check()
-        self.device = torch.device(device)
-        self.W: Dict[str, torch.Tensor] = {}
+        self.meta: Dict[str, tuple] = {}     # per conv: kernel size, un-padded (Cout, Cin)
         self._load(state_dict)
         self._chunk = None          # {"first": bool, "state": {layer key: last two frames}} while slicing
         self.split_size = None      # explicit temporal slice length in sample frames (set_causal_slicing)
+        self.debug = None           # set by apply_model_specific_config (model_configuration.py:1270-1272)
+        self.tensor_offload_device = None
 
     # ---- weights ---------------------------------------------------------
     def _conv_w(self, w, cin_pad=None, cout_pad=None):
@@ -96,7 +100,7 @@ class B200VideoVAE:
                 if ".attentions." in k and old in k:
                     sd[k.replace(old, new)] = sd.pop(k)
                     break
-        W = self.W
+        W: Dict[str, torch.Tensor] = {}
         for k, v in sd.items():
             if k.endswith("upscale_conv.weight"):
                 W[k] = v.to(self.device, torch.bfloat16).reshape(v.shape[0], v.shape[1]).contiguous()
@@ -115,8 +119,8 @@ class B200VideoVAE:
             else:
                 W[k] = self._vec(v) if v.ndim == 1 else v.to(self.device, torch.bfloat16).contiguous()
             if k.endswith(".weight") and v.ndim == 5:
-                W[k + ".k"] = tuple(v.shape[2:])
-                W[k + ".real"] = (v.shape[0], v.shape[1])   # un-padded (Cout, Cin) for the FLOP model
+                self.meta[k + ".k"] = tuple(v.shape[2:])
+                self.meta[k + ".real"] = (v.shape[0], v.shape[1])   # un-padded (Cout, Cin) for the FLOP model
 
         # ResnetBlock3D with a channel change: conv2 and the 1x1x1 conv_shortcut become ONE contraction
         # [hidden ; x] . [W2 ; Wsc] (svr2_conv3d_shortcut_stats_bf16): concatenate the K-major weight rows, sum the biases
@@ -127,12 +131,7 @@ class B200VideoVAE:
             W[p + "conv2+shortcut.bias"] = (W[p + "conv2.bias"].float() + W[p + "conv_shortcut.bias"].float()
                                             ).to(torch.bfloat16).contiguous()
         self.fuse_shortcut = os.environ.get("SVR2_FUSE_SHORTCUT", "1") != "0"      # 0: separate launch (A/B measurements)
-
-    def parameters(self):
-        return iter(v for v in self.W.values() if torch.is_tensor(v))
-
-    def to(self, *a, **k):
-        return self
+        self.W = self._register("w", W)
 
     # ---- temporal slicing state -------------------------------------------
     @property
@@ -175,7 +174,7 @@ class B200VideoVAE:
     def _conv(self, x: Act, prefix: str, *, out_pad=0, residual: Optional[Act] = None, stride_t=1, stride_hw=1,
               cout=None, cin=None, stats=False) -> Act:
         w = self.W[prefix + ".weight"]
-        kt, kh, kw = self.W[prefix + ".weight.k"]
+        kt, kh, kw = self.meta[prefix + ".weight.k"]
         Cout = cout if cout is not None else w.shape[0]
         Cin = cin if cin is not None else x.C
         assert x.pad == kt - 1, f"{prefix}: conv with kt={kt} needs a {kt - 1}-frame halo, got {x.pad}"
@@ -211,8 +210,8 @@ class B200VideoVAE:
             y.stats = (part, slots.value)
             name, extra = "svr2_conv3d_stats_bf16", (lib.ptr(part), part.numel() * 4, ctypes.byref(slots))
         lib.call(name, *args, *extra, lib.stream(),
-                 flops=2.0 * T_out * Ho * Wo * self.W[prefix + ".weight.real"][0] * kt * kh * kw
-                 * self.W[prefix + ".weight.real"][1],
+                 flops=2.0 * T_out * Ho * Wo * self.meta[prefix + ".weight.real"][0] * kt * kh * kw
+                 * self.meta[prefix + ".weight.real"][1],
                  tag=(f"|{Cin}>{w.shape[0]}|k{kt}{kh}{kw}|s{stride_t}{stride_hw}|{T_out}x{Ho}x{Wo}"
                       if (lib.PROFILER is not None and lib.PROFILER.detail) else ""))
         self._halo(y, prefix + ":out")
@@ -235,7 +234,7 @@ class B200VideoVAE:
         """conv2(h) + conv_shortcut(x) as one implicit GEMM over [h ; x] (see _load); statistics for the next GroupNorm."""
         import ctypes
         w, b = self.W[p + "conv2+shortcut.weight"], self.W[p + "conv2+shortcut.bias"]
-        kt, kh, kw = self.W[p + "conv2.weight.k"]
+        kt, kh, kw = self.meta[p + "conv2.weight.k"]
         Cout, C2 = w.shape[0], x.C
         assert h.pad == kt - 1 and (h.T, h.H, h.W) == (x.T, x.H, x.W) and h.C == Cout
         y = Act(h.T, h.H, h.W, Cout, out_pad, self.device)
