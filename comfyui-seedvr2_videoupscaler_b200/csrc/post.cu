@@ -253,6 +253,41 @@ __global__ void __launch_bounds__(256) blend_overlap_f32_kernel(const float4* __
   }
 }
 
+// Spatially tiled VAE (tiled_encode / tiled_decode, attn_video_vae.py:1302-1630): one tile accumulated into the running
+// result with separable edge weights, in bf16 with torch's in-place op order — tile.mul_(wh).mul_(ww); result += tile;
+// count.addcmul_(wh, ww) — i.e. every product / sum is rounded to bf16 where the reference rounds it.
+__global__ void __launch_bounds__(256) tile_accumulate_kernel(const __nv_bfloat16* __restrict__ tile, long long tile_plane,
+                                                              int tile_ld, int planes, int eh, int ew,
+                                                              const __nv_bfloat16* __restrict__ wh,
+                                                              const __nv_bfloat16* __restrict__ ww,
+                                                              __nv_bfloat16* __restrict__ result,
+                                                              __nv_bfloat16* __restrict__ count, int H, int W, int y0,
+                                                              int x0) {
+  const long long n = (long long)planes * eh * ew;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int x = (int)(i % ew), y = (int)((i / ew) % eh);
+    const long long pl = i / ((long long)ew * eh);
+    const float a = __bfloat162float(wh[y]), b = __bfloat162float(ww[x]);
+    const float t = rn(rn(__bfloat162float(tile[pl * tile_plane + (long long)y * tile_ld + x]) * a) * b);
+    const long long ro = (pl * H + (y0 + y)) * W + (x0 + x);
+    result[ro] = __float2bfloat16_rn(__bfloat162float(result[ro]) + t);
+    if (pl == 0) {
+      const long long co = (long long)(y0 + y) * W + (x0 + x);
+      count[co] = __float2bfloat16_rn(fmaf(a, b, __bfloat162float(count[co])));     // addcmul_: one rounding
+    }
+  }
+}
+// result.div_(count.clamp(min=1e-6))
+__global__ void __launch_bounds__(256) tile_normalize_kernel(__nv_bfloat16* __restrict__ result,
+                                                             const __nv_bfloat16* __restrict__ count, int planes,
+                                                             long long hw) {
+  const long long n = (long long)planes * hw;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float c = rn(fmaxf(__bfloat162float(count[i % hw]), 1e-6f));
+    result[i] = __float2bfloat16_rn(__bfloat162float(result[i]) / c);
+  }
+}
+
 inline int grid_for(long long n, int per_block = 256, int waves = 16) {
   long long b = (n + per_block - 1) / per_block;
   const long long cap = (long long)num_sms() * waves;
@@ -389,4 +424,25 @@ extern "C" int svr2_blend_overlap_f32(const float* prev_tail, const float* cur_h
   blend_overlap_f32_kernel<<<dim3(bx, overlap), 256, 0, (cudaStream_t)stream>>>((const float4*)prev_tail, (const float4*)cur_head,
                                                                                  (float4*)out, w_prev, w_cur, vec);
   return check_launch("blend_overlap_f32");
+}
+
+extern "C" int svr2_tile_accumulate_bf16(const void* tile, int64_t tile_plane_stride, int tile_row_stride, int planes,
+                                         int eff_h, int eff_w, const void* weight_h, const void* weight_w, void* result,
+                                         void* count, int H, int W, int y0, int x0, void* stream) {
+  if (planes <= 0 || eff_h <= 0 || eff_w <= 0) return SVR2_OK;
+  if (y0 < 0 || x0 < 0 || y0 + eff_h > H || x0 + eff_w > W)
+    return set_error(SVR2_ERR_ARG, "svr2_tile_accumulate_bf16: tile does not fit the result");
+  const long long n = (long long)planes * eff_h * eff_w;
+  tile_accumulate_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)tile, tile_plane_stride, tile_row_stride, planes, eff_h, eff_w,
+      (const __nv_bfloat16*)weight_h, (const __nv_bfloat16*)weight_w, (__nv_bfloat16*)result, (__nv_bfloat16*)count, H, W,
+      y0, x0);
+  return check_launch("tile_accumulate");
+}
+
+extern "C" int svr2_tile_normalize_bf16(void* result, const void* count, int planes, int64_t hw, void* stream) {
+  if (planes <= 0 || hw <= 0) return SVR2_OK;
+  tile_normalize_kernel<<<grid_for((long long)planes * hw), 256, 0, (cudaStream_t)stream>>>(
+      (__nv_bfloat16*)result, (const __nv_bfloat16*)count, planes, hw);
+  return check_launch("tile_normalize");
 }

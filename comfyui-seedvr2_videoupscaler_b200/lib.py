@@ -59,6 +59,8 @@ SIGNATURES = {
     "svr2_sample_to_image_bf16": [_P, _P, c_int, c_int64, _P],
     "svr2_blend_overlap_bf16": [_P, _P, _P, _P, _P, c_int, c_int64, _P],
     "svr2_blend_overlap_f32": [_P, _P, _P, _P, _P, c_int, c_int64, _P],
+    "svr2_tile_accumulate_bf16": [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "svr2_tile_normalize_bf16": [_P, _P, c_int, c_int64, _P],
     "svr2_resize_scratch_bytes": [c_int, c_int, c_int, c_int],
     "svr2_resize_bicubic_aa_bf16": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int64,
                                     _P],

@@ -364,11 +364,13 @@ class B200VideoVAE(EngineModule):
     @torch.no_grad()
     def decode(self, z: torch.Tensor, return_dict=True, tiled=False, tile_size=None, tile_overlap=None):
         """z (1,16,T,h,w) or (1,16,h,w) -> .sample (1,3,4T-3,8h,8w) bf16 (Decoder3D.forward)."""
-        if tiled:
-            raise NotImplementedError("tiled VAE decode changes results (SURVEY.md a25) and is not part of the B200 path")
+        self._require_cuda("B200VideoVAE.decode")
         squeeze = z.ndim == 4
         if squeeze:
             z = z.unsqueeze(2)
+        if tiled:
+            out = self._tiled(z, False, tile_size or (512, 512), tile_overlap or (64, 64))
+            return VAEOutput(sample=out.squeeze(2) if squeeze else out)
         assert z.shape[0] == 1 and z.shape[1] == 16
         _, _, T, h, w = z.shape
         zin = z[0].to(self.device)
@@ -416,11 +418,13 @@ class B200VideoVAE(EngineModule):
     def encode(self, x: torch.Tensor, return_dict=True, tiled=False, tile_size=None, tile_overlap=None):
         """x (1,3,T,H,W) or (1,3,H,W) in [-1,1] -> .latent (1,16,(T-1)/4+1,H/8,W/8) bf16 = posterior mode
         (Encoder3D.forward + DiagonalGaussianDistribution.mode, attn_video_vae.py:1680-1689)."""
-        if tiled:
-            raise NotImplementedError("tiled VAE encode is not part of the B200 path")
+        self._require_cuda("B200VideoVAE.encode")
         squeeze = x.ndim == 4
         if squeeze:
             x = x.unsqueeze(2)
+        if tiled:
+            out = self._tiled(x, True, tile_size or (512, 512), tile_overlap or (64, 64))
+            return VAEOutput(latent=out.squeeze(2) if squeeze else out, latent_dist=None)
         assert x.shape[0] == 1 and x.shape[1] == 3
         _, _, T, H, Wd = x.shape
         xin = x[0].to(self.device)
@@ -465,6 +469,67 @@ class B200VideoVAE(EngineModule):
         out = torch.empty(1, 16, h.T, h.H, h.W, device=dev, dtype=torch.bfloat16)
         lib.call("svr2_ndhwc_to_ncdhw", lib.ptr(h.buf), 32, 16, h.T, h.H, h.W, lib.ptr(out), 1, lib.stream())
         return out
+
+    # ---- spatial tiling (a25) ------------------------------------------------
+    def _tiled(self, src: torch.Tensor, encode: bool, tile_size, tile_overlap) -> torch.Tensor:
+        """VideoAutoencoderKL.tiled_encode / tiled_decode (attn_video_vae.py:1302-1630): the frame is cut into latent
+        tiles of ``tile_size // 8`` stepping by ``tile - overlap // 8``; every tile runs through the whole (temporally
+        sliced) encoder / decoder on its own and the results are cross-faded with raised-cosine ramps on interior
+        edges — in latent space for encode, in sample space for decode — then normalised by the accumulated weights.
+        Tiling changes results by design (tiles do not see their neighbours); it exists to bound memory.  The seam
+        arithmetic runs in bf16 with the reference's rounding points (``svr2_tile_accumulate_bf16``)."""
+        dev = self.device
+        _, _, _, H, W = src.shape
+        f = 8
+        th, tw = max(1, tile_size[0] // f), max(1, tile_size[1] // f)
+        run = (lambda t: self.encode(t).latent) if encode else (lambda t: self.decode(t).sample)
+        if (encode and H <= tile_size[0] and W <= tile_size[1]) or (not encode and H <= th and W <= tw):
+            return run(src)
+        loh, low = max(0, min(tile_overlap[0] // f, th - 1)), max(0, min(tile_overlap[1] // f, tw - 1))
+        sh, sw = max(1, th - loh), max(1, tw - low)
+        Hl, Wl = ((H + f - 1) // f, (W + f - 1) // f) if encode else (H, W)
+        s = 1 if encode else f                                     # result samples per latent sample
+        ovh, ovw = (loh, low) if encode else tuple(tile_overlap)   # ramp lengths in result samples
+        bf = torch.bfloat16
+
+        def ramp(n):
+            t = torch.linspace(0, 1, steps=n, device=dev, dtype=bf)
+            return 0.5 - 0.5 * torch.cos(t * torch.pi)
+        ramps = (ramp(ovh) if ovh > 0 else None, ramp(ovw) if ovw > 0 else None)
+
+        def weights(n, ov, r, lo, hi):
+            w = torch.ones(n, device=dev, dtype=bf)
+            if ov > 0 and lo:
+                w[:ov] = r[:ov]
+            if ov > 0 and hi:
+                w[-ov:] = 1 - r[:ov]
+            return w
+        result = count = None
+        for y0 in range(0, Hl, sh):
+            y1 = min(y0 + th, Hl)
+            for x0 in range(0, Wl, sw):
+                x1 = min(x0 + tw, Wl)
+                if (y0 > 0 and y1 - y0 <= loh) or (x0 > 0 and x1 - x0 <= low):
+                    continue                                        # wholly inside the previous tile's overlap
+                if encode:
+                    tile = run(src[:, :, :, y0 * f:min(y1 * f, H), x0 * f:min(x1 * f, W)])
+                else:
+                    tile = run(src[:, :, :, y0:y1, x0:x1])
+                tile = tile.contiguous()
+                if result is None:
+                    C, T = tile.shape[1], tile.shape[2]
+                    result = torch.zeros(1, C, T, Hl * s, Wl * s, device=dev, dtype=bf)
+                    count = torch.zeros(Hl * s, Wl * s, device=dev, dtype=bf)
+                eh = min((y1 - y0) * s, tile.shape[3], Hl * s - y0 * s)
+                ew = min((x1 - x0) * s, tile.shape[4], Wl * s - x0 * s)
+                wh = weights(eh, max(0, min(ovh, eh - 1)), ramps[0], y0 > 0, y1 < Hl)
+                ww = weights(ew, max(0, min(ovw, ew - 1)), ramps[1], x0 > 0, x1 < Wl)
+                lib.call("svr2_tile_accumulate_bf16", lib.ptr(tile), tile.shape[3] * tile.shape[4], tile.shape[4],
+                         C * T, eh, ew, lib.ptr(wh), lib.ptr(ww), lib.ptr(result), lib.ptr(count), Hl * s, Wl * s,
+                         y0 * s, x0 * s, lib.stream(), nbytes=6.0 * C * T * eh * ew)
+        lib.call("svr2_tile_normalize_bf16", lib.ptr(result), lib.ptr(count), result.shape[1] * result.shape[2],
+                 Hl * s * Wl * s, lib.stream(), nbytes=4.0 * result.numel())
+        return result
 
     # reference wrapper surface used by the pipeline (model_configuration.py:1247-1276)
     def preprocess(self, x):

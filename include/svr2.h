@@ -194,6 +194,15 @@ int svr2_blend_overlap_bf16(const void* prev_tail, const void* cur_head, void* o
 int svr2_blend_overlap_f32(const float* prev_tail, const float* cur_head, float* out, const float* w_prev,
                            const float* w_cur, int overlap, int64_t frame_elems, void* stream);
 
+/* ---- Spatially tiled VAE seams (VideoAutoencoderKL.tiled_encode / tiled_decode, attn_video_vae.py:1302-1630; optional,
+ * off in every BASELINE config).  Accumulate one tile [planes, eff_h, eff_w] (plane / row strides in elements) into
+ * result [planes, H, W] at (y0, x0) with separable bf16 edge weights, and its weight into count [H, W]; rounding points
+ * are torch's: tile.mul_(wh).mul_(ww); result += tile; count.addcmul_(wh, ww).  Then result.div_(count.clamp(1e-6)). */
+int svr2_tile_accumulate_bf16(const void* tile, int64_t tile_plane_stride, int tile_row_stride, int planes, int eff_h,
+                              int eff_w, const void* weight_h, const void* weight_w, void* result, void* count, int H,
+                              int W, int y0, int x0, void* stream);
+int svr2_tile_normalize_bf16(void* result, const void* count, int planes, int64_t hw, void* stream);
+
 /* ---- Clip pre-processing (prepare_video_transforms, src/core/generation_utils.py:72-84).
  * Antialiased bicubic resize (torchvision resize -> torch _upsample_bicubic2d_aa semantics, fp32 accumulation, result
  * rounded to bf16) of frames given as [T,h,w,cin] (channels_last != 0, first 3 channels) or [T,3,h,w]; in_dtype

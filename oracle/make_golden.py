@@ -141,6 +141,43 @@ def run_vae_cases():
                             meta=np.array(shp))
 
 
+# ---- spatially tiled VAE (attn_video_vae.py:1302-1630): name -> (kind, shape, tile_size, tile_overlap)
+TILED_CASES = {
+    "vae_tiled_dec_t2": ("decode", (2, 7, 11), (32, 32), (16, 16)),     # latent 7x11, tiles of 4 with 2 overlap, ragged edge
+    "vae_tiled_enc_t5": ("encode", (5, 56, 88), (32, 32), (16, 16)),
+    "vae_tiled_dec_img": ("decode", (1, 9, 6), (48, 32), (8, 24)),      # single image, anisotropic tiles / overlaps
+}
+
+
+def run_tiled_cases():
+    sd = pkg.weights.synth_vae_state_dict(seed=4321, dtype=torch.float16)
+    sd32 = {k: v.float() for k, v in sd.items()}
+    vae = build_ref_vae()
+    vae.load_state_dict(dict(sd32), strict=True)
+    vae.set_causal_slicing(split_size=4, memory_device="same")
+    vae.debug, vae.tensor_offload_device = None, None          # set by apply_model_specific_config in the pipeline
+    for name, (kind, shp, tile, ov) in TILED_CASES.items():
+        g = torch.Generator().manual_seed(7)
+        with torch.no_grad():
+            if kind == "decode":
+                z = torch.randn(1, 16, *shp, generator=g)
+                ref = vae.decode(z, tiled=True, tile_size=tile, tile_overlap=ov).sample
+                ora = vae_oracle.tiled_decode(sd32, z, tile, ov)
+            else:
+                x = torch.rand(1, 3, *shp, generator=g) * 2 - 1
+                ref = vae.encode(x, tiled=True, tile_size=tile, tile_overlap=ov).latent
+                ora = vae_oracle.tiled_encode(sd32, x, tile, ov)
+        if ref.ndim == 4:
+            ref = ref.unsqueeze(2)
+        if ora.ndim == 4:
+            ora = ora.unsqueeze(2)
+        err = (ora - ref).abs().max().item()
+        print(f"[{name}] out {tuple(ref.shape)} oracle-vs-reference max|d|={err:.2e}")
+        assert err < 2e-4 * max(ref.abs().max().item(), 1.0), name
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), out=ref.numpy().astype(np.float32),
+                            meta=np.array(list(shp) + list(tile) + list(ov)))
+
+
 # ---- post-decode colour correction (src/utils/color_fix.py): name -> (T, H, W)
 COLOR_CASES = {
     "color_t2_40x56": (2, 40, 56),        # min(H,W)//8 = 5 caps the dilation of levels 3, 4
@@ -295,10 +332,13 @@ def run_pre_cases():
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
+    if "--tiled-only" in sys.argv:
+        return run_tiled_cases()
     if "--color-only" not in sys.argv and "--pre-only" not in sys.argv:
         for name in DIT_CASES:
             run_dit_case(name)
         run_vae_cases()
+        run_tiled_cases()
     if "--pre-only" not in sys.argv:
         run_color_cases()
     if "--color-only" not in sys.argv:

@@ -193,3 +193,92 @@ def pad_video_temporal(videos: torch.Tensor, count: int = 0, temporal_dim: int =
         rev = v[1:count + 1].flip(0) if prepend else v[-count - 1:-1].flip(0)
         out = torch.cat([rev, v] if prepend else [v, rev], 0)
     return out.movedim(0, temporal_dim)
+
+
+# --------------------------------------------------------------------------
+# spatial tiling (attn_video_vae.py:1302-1630) — optional, off in every BASELINE config; changes results by design
+# --------------------------------------------------------------------------
+def _tile_plan(extent_h: int, extent_w: int, tile_hw, overlap_hw):
+    """Latent-space tile boxes in the reference's visiting order (rows, then columns), skipping a trailing tile that
+    lies wholly inside the previous tile's overlap (:1366-1371, :1532-1536)."""
+    (th, tw), (oh, ow) = tile_hw, overlap_hw
+    sh, sw = max(1, th - oh), max(1, tw - ow)
+    boxes = []
+    for y0 in range(0, extent_h, sh):
+        y1 = min(y0 + th, extent_h)
+        for x0 in range(0, extent_w, sw):
+            x1 = min(x0 + tw, extent_w)
+            if (y0 > 0 and y1 - y0 <= oh) or (x0 > 0 and x1 - x0 <= ow):
+                continue
+            boxes.append((y0, y1, x0, x1))
+    return boxes
+
+
+def _edge_weights(n: int, ov: int, ramp, fade_lo: bool, fade_hi: bool, like):
+    """Separable blend weight of one tile axis: 1 inside, raised-cosine ramp over ``ov`` samples on interior edges only."""
+    wgt = torch.ones(n, device=like.device, dtype=like.dtype)
+    if ov > 0:
+        if fade_lo:
+            wgt[:ov] = ramp[:ov]
+        if fade_hi:
+            wgt[-ov:] = 1 - ramp[:ov]
+    return wgt
+
+
+def _raised_cosine(steps: int, like):
+    t = torch.linspace(0, 1, steps=steps, device=like.device, dtype=like.dtype)
+    return 0.5 - 0.5 * torch.cos(t * torch.pi)
+
+
+def _blend_tiles(boxes, tiles, scale: int, ov_hw, ramp_hw, extent_hw, like):
+    """Accumulate weighted tiles and normalise by the accumulated weights, in the tiles' dtype with the reference's
+    in-place op order (mul_ by the row weights, mul_ by the column weights, +=, addcmul_, div_ by clamp(count))."""
+    (H, W), (ovh, ovw) = extent_hw, ov_hw
+    first = tiles[0]
+    res = torch.zeros(first.shape[0], first.shape[1], first.shape[2], H * scale, W * scale, device=like.device, dtype=first.dtype)
+    cnt = torch.zeros(1, 1, 1, H * scale, W * scale, device=like.device, dtype=first.dtype)
+    for (y0, y1, x0, x1), tile in zip(boxes, tiles):
+        hh = min((y1 - y0) * scale, tile.shape[3], res.shape[3] - y0 * scale)
+        ww = min((x1 - x0) * scale, tile.shape[4], res.shape[4] - x0 * scale)
+        tile = tile[:, :, : res.shape[2], :hh, :ww].clone()
+        wh = _edge_weights(hh, max(0, min(ovh, hh - 1)), ramp_hw[0], y0 > 0, y1 < H, tile).view(1, 1, 1, hh, 1)
+        wv = _edge_weights(ww, max(0, min(ovw, ww - 1)), ramp_hw[1], x0 > 0, x1 < W, tile).view(1, 1, 1, 1, ww)
+        tile.mul_(wh).mul_(wv)
+        ys, xs = y0 * scale, x0 * scale
+        res[:, :, : tile.shape[2], ys:ys + hh, xs:xs + ww] += tile
+        cnt[:, :, :, ys:ys + hh, xs:xs + ww].addcmul_(wh, wv)
+    return res.div_(cnt.clamp(min=1e-6))
+
+
+def tiled_decode(sd, z: torch.Tensor, tile_size=(512, 512), tile_overlap=(64, 64), mode: str = "fp32", decode_fn=None):
+    """VideoAutoencoderKL.tiled_decode (attn_video_vae.py:1472-1630): latent tiles of tile_size // 8, stride = tile -
+    overlap // 8, every tile decoded on its own, blended in sample space with ramps of ``tile_overlap`` samples."""
+    dec = decode_fn or (lambda t: vae_decode(sd, t, mode))
+    _, _, _, H, W = z.shape
+    th, tw = max(1, tile_size[0] // 8), max(1, tile_size[1] // 8)
+    if H <= th and W <= tw:
+        return dec(z)
+    loh, low = max(0, min(tile_overlap[0] // 8, th - 1)), max(0, min(tile_overlap[1] // 8, tw - 1))
+    boxes = _tile_plan(H, W, (th, tw), (loh, low))
+    zt = z.to(_dt(mode)) if decode_fn is None else z
+    ramps = (_raised_cosine(tile_overlap[0], zt) if tile_overlap[0] > 0 else None,
+             _raised_cosine(tile_overlap[1], zt) if tile_overlap[1] > 0 else None)
+    tiles = [dec(z[:, :, :, y0:y1, x0:x1]) for (y0, y1, x0, x1) in boxes]
+    return _blend_tiles(boxes, tiles, 8, tile_overlap, ramps, (H, W), zt)
+
+
+def tiled_encode(sd, x: torch.Tensor, tile_size=(512, 512), tile_overlap=(64, 64), mode: str = "fp32", encode_fn=None):
+    """VideoAutoencoderKL.tiled_encode (attn_video_vae.py:1302-1470): sample-space crops of whole latent tiles, every
+    crop encoded on its own, blended in latent space with ramps of ``tile_overlap // 8`` latent samples."""
+    enc = encode_fn or (lambda t: vae_encode(sd, t, mode))
+    _, _, _, H, W = x.shape
+    if H <= tile_size[0] and W <= tile_size[1]:
+        return enc(x)
+    th, tw = max(1, tile_size[0] // 8), max(1, tile_size[1] // 8)
+    loh, low = max(0, min(tile_overlap[0] // 8, th - 1)), max(0, min(tile_overlap[1] // 8, tw - 1))
+    Hl, Wl = (H + 7) // 8, (W + 7) // 8
+    boxes = _tile_plan(Hl, Wl, (th, tw), (loh, low))
+    xt = x.to(_dt(mode)) if encode_fn is None else x
+    ramps = (_raised_cosine(loh, xt) if loh > 0 else None, _raised_cosine(low, xt) if low > 0 else None)
+    tiles = [enc(x[:, :, :, y0 * 8:min(y1 * 8, H), x0 * 8:min(x1 * 8, W)]) for (y0, y1, x0, x1) in boxes]
+    return _blend_tiles(boxes, tiles, 1, (loh, low), ramps, (Hl, Wl), xt)

@@ -243,3 +243,32 @@ def test_dit_medium_size_vs_oracle(pkg):
     refbf = dit_oracle.dit_forward(sd32, cfg, vid.cpu(), txt.cpu(), T, H, W, mode="ref_bf16")
     p_eng, p_ref = psnr(out, ref32), psnr(refbf, ref32)
     assert p_eng >= 50.0, f"DiT medium: {p_eng:.1f} dB vs fp32 oracle (reference-bf16 flow: {p_ref:.1f} dB)"
+
+
+def test_vae_tiled_vs_reference_golden_and_oracle(vae_pair):
+    """tiled=True (a25; attn_video_vae.py:1302-1630): the engine's tile loop + seam kernels vs the goldens the reference's
+    own tiled paths produced, and its seam arithmetic vs the oracle's bf16 blend fed with the ENGINE's own tiles
+    (isolates plan / weights / rounding order: must agree to a bf16 ulp)."""
+    from oracle.make_golden import TILED_CASES
+    eng, sd32 = vae_pair
+    for name, (kind, shp, tile, ov) in TILED_CASES.items():
+        g = torch.Generator().manual_seed(7)
+        gold = torch.from_numpy(np.load(os.path.join(GOLD, name + ".npz"))["out"])
+        if kind == "decode":
+            src = torch.randn(1, 16, *shp, generator=g).cuda()
+            out = eng.decode(src, tiled=True, tile_size=tile, tile_overlap=ov).sample
+            obf = vae_oracle.tiled_decode(sd32, src, tile, ov, mode="ref_bf16")
+            seam = vae_oracle.tiled_decode(None, src.bfloat16(), tile, ov, decode_fn=lambda t: eng.decode(t).sample)
+        else:
+            src = (torch.rand(1, 3, *shp, generator=g) * 2 - 1).cuda()
+            out = eng.encode(src, tiled=True, tile_size=tile, tile_overlap=ov).latent
+            obf = vae_oracle.tiled_encode(sd32, src, tile, ov, mode="ref_bf16")
+            seam = vae_oracle.tiled_encode(None, src.bfloat16(), tile, ov, encode_fn=lambda t: eng.encode(t).latent)
+        if out.ndim == 4:
+            out, obf, seam = out.unsqueeze(2), obf.unsqueeze(2), (seam.unsqueeze(2) if seam.ndim == 4 else seam)
+        assert out.shape == gold.shape, name
+        p_eng, p_ref = psnr(out, gold), psnr(obf, gold)
+        assert p_eng >= 42.0 and p_eng >= p_ref - 3.0, f"{name}: engine {p_eng:.1f} dB, reference bf16 flow {p_ref:.1f} dB"
+        d = (out.float() - seam.float()).abs()
+        assert (d == 0).float().mean() > 0.99 and d.max() <= 2 ** -6 * max(1.0, seam.abs().max().item()), \
+            f"{name}: seam arithmetic differs from the reference's op order ({(d == 0).float().mean():.4f} equal, max {d.max():.4f})"

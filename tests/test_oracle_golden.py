@@ -166,3 +166,18 @@ def test_hsv_and_adaptive_oracle_match_reference_as_distributions():
         assert 10 * torch.log10(4.0 / ((out - ref) ** 2).mean()) > 35.0
     c01 = ((c2.float() + 1.0) * 0.5).clamp(0.0, 1.0)
     assert (color_oracle.hsv_to_rgb(color_oracle.rgb_to_hsv(c01)) - c01).abs().max() < 1e-5
+
+
+def test_tiled_vae_oracle_matches_reference_golden(pkg):
+    """tiled_encode / tiled_decode restatement (attn_video_vae.py:1302-1630) vs goldens the reference's own tiled paths
+    produced (oracle/make_golden.py --tiled-only): fp32, same inputs."""
+    from oracle.make_golden import TILED_CASES
+    sd32 = {k: v.float() for k, v in pkg.weights.synth_vae_state_dict(seed=4321, dtype=torch.float16).items()}
+    for name, (kind, shp, tile, ov) in TILED_CASES.items():
+        g = torch.Generator().manual_seed(7)
+        gold = torch.from_numpy(np.load(os.path.join(GOLD, name + ".npz"))["out"])
+        if kind == "decode":
+            out = vae_oracle.tiled_decode(sd32, torch.randn(1, 16, *shp, generator=g), tile, ov)
+        else:
+            out = vae_oracle.tiled_encode(sd32, torch.rand(1, 3, *shp, generator=g) * 2 - 1, tile, ov)
+        assert out.shape == gold.shape and (out - gold).abs().max() < 2e-4 * max(gold.abs().max().item(), 1.0), name
