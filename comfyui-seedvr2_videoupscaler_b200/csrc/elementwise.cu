@@ -123,8 +123,9 @@ __global__ void __launch_bounds__(256) qk_norm_rope_window_kernel(
     const int32_t* __restrict__ row_src, const int32_t* __restrict__ row_rope, const float* __restrict__ cos_tab,
     const float* __restrict__ sin_tab, int nfreq, const float* __restrict__ wq_vid, const float* __restrict__ wk_vid,
     const float* __restrict__ wq_txt, const float* __restrict__ wk_txt, float eps, int heads,
-    __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, __nv_bfloat16* __restrict__ v) {
-  const long long r = blockIdx.x;
+    __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, __nv_bfloat16* __restrict__ v,
+    const int32_t* __restrict__ row_list) {
+  const long long r = row_list ? (long long)row_list[blockIdx.x] : (long long)blockIdx.x;   // optional subset of the rows
   const int src = row_src[r];
   const bool is_txt = src < 0;
   const int inner = heads * 128;
@@ -182,8 +183,9 @@ __global__ void __launch_bounds__(256) qk_norm_rope_window_v2_kernel(
     const int32_t* __restrict__ row_src, const int32_t* __restrict__ row_rope, const float* __restrict__ cos_tab,
     const float* __restrict__ sin_tab, int nfreq, const float* __restrict__ wq_vid, const float* __restrict__ wk_vid,
     const float* __restrict__ wq_txt, const float* __restrict__ wk_txt, float eps, int heads,
-    __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, __nv_bfloat16* __restrict__ v) {
-  const long long r = blockIdx.x;
+    __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, __nv_bfloat16* __restrict__ v,
+    const int32_t* __restrict__ row_list) {
+  const long long r = row_list ? (long long)row_list[blockIdx.x] : (long long)blockIdx.x;   // optional subset of the rows
   const int src = row_src[r];
   const bool is_txt = src < 0;
   const int inner = heads * 128;
@@ -814,12 +816,11 @@ extern "C" int svr2_rmsnorm_ada_bf16(const void* x, void* y, int rows, int dim, 
   return check_launch("rmsnorm_ada");
 }
 
-extern "C" int svr2_qk_norm_rope_window_bf16(const void* qkv_vid, const void* qkv_txt, const int32_t* row_src,
-                                             const int32_t* row_rope, const float* cos_tab, const float* sin_tab,
-                                             int nfreq, const float* wq_vid, const float* wk_vid, const float* wq_txt,
-                                             const float* wk_txt, float eps, int total, int heads, void* q, void* k,
-                                             void* v, void* stream) {
-  if (total <= 0) return SVR2_OK;
+static int qk_norm_rope_launch(const void* qkv_vid, const void* qkv_txt, const int32_t* row_src, const int32_t* row_rope,
+                               const float* cos_tab, const float* sin_tab, int nfreq, const float* wq_vid,
+                               const float* wk_vid, const float* wq_txt, const float* wk_txt, float eps, int n_rows,
+                               int heads, void* q, void* k, void* v, const int32_t* row_list, void* stream) {
+  if (n_rows <= 0) return SVR2_OK;
   if (6 * nfreq > 128) return set_error(SVR2_ERR_ARG, "rope: 6*nfreq > head_dim");
   const int threads = heads >= 8 ? 256 : 32 * heads;   // 8 warps loop over the heads (one warp per head was slower: 54 vs 34 ms)
   static int v2 = -1;
@@ -828,10 +829,31 @@ extern "C" int svr2_qk_norm_rope_window_bf16(const void* qkv_vid, const void* qk
     v2 = (e && e[0] == 'v' && e[1] == '1') ? 0 : 1;     // v2: 34.4 -> 30.2 ms per 4K step on the same box; SVR2_QK_ROPE=v1 for A/B
   }
   auto kern = v2 ? qk_norm_rope_window_v2_kernel : qk_norm_rope_window_kernel;
-  kern<<<total, threads, 0, (cudaStream_t)stream>>>(
+  kern<<<n_rows, threads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)qkv_vid, (const __nv_bfloat16*)qkv_txt, row_src, row_rope, cos_tab, sin_tab, nfreq, wq_vid,
-      wk_vid, wq_txt, wk_txt, eps, heads, (__nv_bfloat16*)q, (__nv_bfloat16*)k, (__nv_bfloat16*)v);
+      wk_vid, wq_txt, wk_txt, eps, heads, (__nv_bfloat16*)q, (__nv_bfloat16*)k, (__nv_bfloat16*)v, row_list);
   return check_launch("qk_norm_rope_window");
+}
+
+extern "C" int svr2_qk_norm_rope_window_bf16(const void* qkv_vid, const void* qkv_txt, const int32_t* row_src,
+                                             const int32_t* row_rope, const float* cos_tab, const float* sin_tab,
+                                             int nfreq, const float* wq_vid, const float* wk_vid, const float* wq_txt,
+                                             const float* wk_txt, float eps, int total, int heads, void* q, void* k,
+                                             void* v, void* stream) {
+  return qk_norm_rope_launch(qkv_vid, qkv_txt, row_src, row_rope, cos_tab, sin_tab, nfreq, wq_vid, wk_vid, wq_txt, wk_txt,
+                             eps, total, heads, q, k, v, nullptr, stream);
+}
+
+// Same, for the subset of output rows listed in row_list (the text rows of every window when the video rows come out
+// of svr2_linear_qkv_rope_bf16's epilogue).
+extern "C" int svr2_qk_norm_rope_rows_bf16(const void* qkv_vid, const void* qkv_txt, const int32_t* row_src,
+                                           const int32_t* row_rope, const float* cos_tab, const float* sin_tab, int nfreq,
+                                           const float* wq_vid, const float* wk_vid, const float* wq_txt,
+                                           const float* wk_txt, float eps, const int32_t* row_list, int n_rows, int heads,
+                                           void* q, void* k, void* v, void* stream) {
+  if (!row_list) return set_error(SVR2_ERR_ARG, "svr2_qk_norm_rope_rows_bf16: row_list must not be NULL");
+  return qk_norm_rope_launch(qkv_vid, qkv_txt, row_src, row_rope, cos_tab, sin_tab, nfreq, wq_vid, wk_vid, wq_txt, wk_txt,
+                             eps, n_rows, heads, q, k, v, row_list, stream);
 }
 
 extern "C" int svr2_txt_window_mean_bf16(const void* in, void* out, int n_win, int l, int dim, void* stream) {

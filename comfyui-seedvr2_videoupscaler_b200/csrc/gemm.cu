@@ -69,6 +69,16 @@ struct GemmParams {
   void* out;
   float4* stat_partial;           // conv only: [frame][slot][N/8] (sum0, sq0, sum1, sq1) of the stored values, or null
   int stat_slots;                 // slots per frame (tiles per frame x warps covering distinct rows)
+  // ---- KIND_QKV*: fused q/k RMSNorm + RoPE + window scatter (out = q, out2 = k, out3 = v, each [rows, inner])
+  void* out2;
+  void* out3;
+  const int32_t* tok_dst;         // [M] destination row (window order) of every token
+  const int32_t* tok_rope;        // [M,3] rows of the cos/sin tables per axis, or -1
+  const float* rope_cos;          // [R, nfreq]
+  const float* rope_sin;
+  const float* qk_weight;         // [2][128]: q-norm weight, k-norm weight
+  float qk_eps;
+  int qkv_inner;                  // heads * 128
 };
 
 enum : int {
@@ -144,7 +154,8 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
   n = n0 + (r - m * gsz);
 }
 
-enum : int { KIND_BF16 = 0, KIND_SWIGLU = 1, KIND_F32 = 2, KIND_ROWSTAT = 3, KIND_PEXP = 4 };
+enum : int { KIND_BF16 = 0, KIND_SWIGLU = 1, KIND_F32 = 2, KIND_ROWSTAT = 3, KIND_PEXP = 4,
+             KIND_QKV21 = 5, KIND_QKV10 = 6 };   // QKV projection + q/k RMSNorm + RoPE (21 / 10 frequencies per axis) + window scatter
 
 // One tile's output row of a thread: destination offset (elements), validity, halo duplication.
 struct RowDest {
@@ -550,7 +561,88 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int m = m_blk * BLOCK_M + row;
         row_lse = (m < p.M) ? gate[m] : 0.f;
       }
-      if constexpr (KIND == KIND_ROWSTAT) {
+      if constexpr (KIND == KIND_QKV21 || KIND == KIND_QKV10) {
+        // NaSwinAttention between the QKV projection and the attention call (mmattn.py:199-248, rope.py:116-176), in
+        // the epilogue: a 256-column tile is two heads of q, of k or of v, so this warp's 128 columns are ONE head of
+        // ONE row per thread — per-head RMSNorm is a thread-local sum, RoPE pairs are adjacent registers.  The bf16
+        // rounding of the projection output comes first (the reference normalises the bf16 Linear output in fp32).
+        static_assert(BLOCK_N == 256, "QKV epilogue needs 256-column tiles");
+        constexpr int NF = KIND == KIND_QKV21 ? 21 : 10;
+        const int tpw = p.qkv_inner / 256;               // n-tiles per q / k / v
+        const int which = n_blk / tpw;                   // 0 q, 1 k, 2 v
+        const int m = m_blk * BLOCK_M + row;
+        const bool rvalid = (m < p.M) && !(TWO && m_blk >= p.num_m_tiles);
+        uint32_t pk[64];
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 64) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(t_addr + col_lo + c0, v0);
+          tmem_ld32(t_addr + col_lo + c0 + 32, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            pk[c0 / 2 + i] = pack_bf16x2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+            pk[c0 / 2 + 16 + i] = pack_bf16x2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+          }
+        }
+        tc_fence_before();
+        tmem_empty_arrive(&tmem_empty[acc]);
+        if (which < 2) {
+          float ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float lo = __uint_as_float(pk[i] << 16), hi = __uint_as_float(pk[i] & 0xffff0000u);
+            ss = fmaf(lo, lo, ss);
+            ss = fmaf(hi, hi, ss);
+          }
+          const float rr = 1.0f / sqrtf(ss * (1.0f / 128.0f) + p.qk_eps);
+          const float2* wn = reinterpret_cast<const float2*>(p.qk_weight + which * 128);
+          int ri[3] = {-1, -1, -1};
+          if (rvalid) {
+            ri[0] = p.tok_rope[(long long)m * 3 + 0];
+            ri[1] = p.tok_rope[(long long)m * 3 + 1];
+            ri[2] = p.tok_rope[(long long)m * 3 + 2];
+          }
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float2 w2 = __ldg(wn + i);
+            const float x0 = __uint_as_float(pk[i] << 16) * rr * w2.x;
+            const float x1 = __uint_as_float(pk[i] & 0xffff0000u) * rr * w2.y;
+            float y0 = x0, y1 = x1;
+            if (i < 3 * NF) {                        // compile-time: pairs 3*NF..63 are not rotated
+              const int tr = ri[i / NF];
+              if (tr >= 0) {
+                const float c = __ldg(p.rope_cos + tr * NF + (i % NF)), sn = __ldg(p.rope_sin + tr * NF + (i % NF));
+                y0 = x0 * c - x1 * sn;               // interleaved pairs: (x0, x1) -> (x0 c - x1 s, x1 c + x0 s)
+                y1 = x1 * c + x0 * sn;
+              }
+            }
+            pk[i] = pack_bf16x2(y0, y1);
+          }
+        }
+        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(which == 0 ? p.out : (which == 1 ? p.out2 : p.out3));
+        const long long roff = rvalid ? (long long)p.tok_dst[m] * p.qkv_inner + (long long)(n_blk - which * tpw) * 256 : 0;
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(slab + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_uint4(pk[ph * 32 + 4 * c], pk[ph * 32 + 4 * c + 1], pk[ph * 32 + 4 * c + 2], pk[ph * 32 + 4 * c + 3]);
+          __syncwarp();
+          const int ch = lane & 7, rsub = lane >> 3;       // 8 x 16-byte chunks per staged row, 4 rows per access
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            const long long off = __shfl_sync(0xffffffffu, roff, r);
+            const int ok = __shfl_sync(0xffffffffu, (int)rvalid, r);
+            if (ok) {
+              const uint4 d = *reinterpret_cast<const uint4*>(slab + r * 128 + ((ch ^ (r & 7)) << 4));
+              *reinterpret_cast<uint4*>(ob + off + col_lo + ph * 64 + ch * 8) = d;
+            }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (KIND == KIND_ROWSTAT) {
         // attention pass 1: thread-local online (max, sum exp2) over this warp's columns; no staging
         float mx = -INFINITY, sum = 0.f;
         if (active) {
@@ -1091,6 +1183,44 @@ extern "C" int svr2_linear_bf16(const void* a, int64_t lda, const void* w, int64
     return set_error(SVR2_ERR_ARG, "EPI_ROWSTAT: ldc (float2 slots per row) must be >= svr2_rowstat_slots(N)");
   if ((p.epi & EPI_RESIDUAL) && !residual) return set_error(SVR2_ERR_ARG, "EPI_RESIDUAL without residual");
   return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream, pair);
+}
+
+// QKV projection with NaSwinAttention's q/k RMSNorm + RoPE + window partition fused into the epilogue
+// (mmattn.py:173,199-248; rope.py:116-176): a [M, K] x w [3*heads*128, K]^T; token m's q/k/v rows land at row
+// tok_dst[m] of q / k / v ([rows, heads*128], window order).  heads must be even (a 256-column tile = 2 heads).
+extern "C" int svr2_linear_qkv_rope_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int heads, int K,
+                                         const int32_t* tok_dst, const int32_t* tok_rope, const float* cos_tab,
+                                         const float* sin_tab, int nfreq, const float* qk_weight, float eps, void* q,
+                                         void* k, void* v, void* stream) {
+  if (M <= 0 || K <= 0 || heads <= 0) return set_error(SVR2_ERR_ARG, "svr2_linear_qkv_rope_bf16: empty problem");
+  if (heads & 1) return set_error(SVR2_ERR_ARG, "svr2_linear_qkv_rope_bf16: heads must be even");
+  if (nfreq != 21 && nfreq != 10) return set_error(SVR2_ERR_ARG, "svr2_linear_qkv_rope_bf16: nfreq must be 21 (3B) or 10 (7B)");
+  if ((lda % 8) || (ldw % 8)) return set_error(SVR2_ERR_ARG, "svr2_linear_qkv_rope_bf16: lda/ldw must be multiples of 8");
+  const int inner = heads * 128, N = 3 * inner, bn = 256;
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const bool pair = want_pair(bn, 0, num_m);
+  CUtensorMap ta, tb;
+  uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)lda * 2};
+  uint32_t ba[2] = {BLOCK_K, BLOCK_M};
+  int rc = make_tmap_bf16(&ta, a, 2, da, sa, ba);
+  if (rc) return rc;
+  uint64_t db[2] = {(uint64_t)K, (uint64_t)N}, sb[1] = {(uint64_t)ldw * 2};
+  uint32_t bb[2] = {BLOCK_K, (uint32_t)(pair ? bn / 2 : bn)};
+  rc = make_tmap_bf16(&tb, w, 2, db, sb, bb);
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.num_m_tiles = num_m;
+  p.num_n_tiles = N / bn;
+  p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  p.a_mode = 0;
+  p.out = q; p.out2 = k; p.out3 = v;
+  p.tok_dst = tok_dst; p.tok_rope = tok_rope;
+  p.rope_cos = cos_tab; p.rope_sin = sin_tab;
+  p.qk_weight = qk_weight; p.qk_eps = eps; p.qkv_inner = inner;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nfreq == 21) return pair ? launch_gemm<256, KIND_QKV21, false, true>(ta, tb, p, s) : launch_gemm<256, KIND_QKV21>(ta, tb, p, s);
+  return pair ? launch_gemm<256, KIND_QKV10, false, true>(ta, tb, p, s) : launch_gemm<256, KIND_QKV10>(ta, tb, p, s);
 }
 
 // number of (max, sum) float2 partial slots per row that EPI_ROWSTAT writes for a given N

@@ -96,6 +96,9 @@ class WindowLayout:
     row_rope: torch.Tensor     # int32 [total,3] rows of the cos/sin tables (or -1)
     out_row_map: torch.Tensor  # int32 [total]   video rows -> token idx, text rows -> L + w*l + j
     attn_flops: float = 0.0    # sum over windows of 4 * len^2 * 128 (per head)
+    tok_dst: torch.Tensor = None    # int32 [L]    window-order row of every video token (inverse of row_src)
+    tok_rope: torch.Tensor = None   # int32 [L,3]  row_rope in token order
+    txt_rows: torch.Tensor = None   # int32 [n_win*l] window-order rows that hold text tokens
 
 
 def build_layout(T: int, Hp: int, Wp: int, l: int, shifted: bool, variant: str, device) -> Tuple[WindowLayout, dict]:
@@ -130,11 +133,20 @@ def build_layout(T: int, Hp: int, Wp: int, l: int, shifted: bool, variant: str, 
     lens_t = torch.tensor(lens, dtype=torch.int64)
     cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
     cu[1:] = lens_t.cumsum(0).int()
+    src_all, rope_all = torch.cat(src), torch.cat(rope)
+    rows = torch.arange(src_all.numel())
+    is_vid = src_all >= 0
+    tok_dst = torch.empty(L, dtype=torch.int64)
+    tok_dst[src_all[is_vid]] = rows[is_vid]                  # the windows partition the tokens: a bijection
+    tok_rope = torch.empty(L, 3, dtype=torch.int64)
+    tok_rope[src_all[is_vid]] = rope_all[is_vid]
     lay = WindowLayout(
         n_win=len(boxes), total=int(lens_t.sum()), max_len=int(lens_t.max()),
         cu_seqlens=cu.to(device), row_src=torch.cat(src).int().to(device),
         row_rope=torch.cat(rope).int().contiguous().to(device), out_row_map=torch.cat(omap).int().to(device),
-        attn_flops=float((lens_t.double() ** 2).sum()) * 4 * 128)
+        attn_flops=float((lens_t.double() ** 2).sum()) * 4 * 128,
+        tok_dst=tok_dst.int().to(device), tok_rope=tok_rope.int().contiguous().to(device),
+        txt_rows=rows[~is_vid].int().to(device))
     return lay, size_rows
 
 
@@ -176,6 +188,10 @@ class B200NaDiT(EngineModule):
         self._layouts: Dict[tuple, tuple] = {}
         self.attention = FlashAttentionVarlen()
         self._load(state_dict)
+        import os
+        # the fused QKV epilogue needs 256-column tiles to be whole head pairs and one of the two shipped RoPE widths
+        self.fuse_qkv = (cfg["heads"] % 2 == 0 and os.environ.get("SVR2_FUSE_QKV", "1") != "0"
+                         and self.rope_freqs[0].numel() in (21, 10))
 
     def _device_state_moved(self):
         if hasattr(self, "_layouts"):
@@ -206,7 +222,7 @@ class B200NaDiT(EngineModule):
             for s in ("vid", "txt"):
                 key = "all" if shared else s
                 if shared and s == "txt":   # alias
-                    for n in ("qkv.w", "out.w", "out.b", "nq", "nk", "mlp_in.w", "mlp_in.b", "mlp_out.w", "mlp_out.b"):
+                    for n in ("qkv.w", "out.w", "out.b", "nq", "nk", "nqk", "mlp_in.w", "mlp_in.b", "mlp_out.w", "mlp_out.b"):
                         if f"{i}.vid.{n}" in W:
                             W[f"{i}.txt.{n}"] = W[f"{i}.vid.{n}"]
                     continue
@@ -215,6 +231,7 @@ class B200NaDiT(EngineModule):
                 W[f"{i}.{s}.out.b"] = self._w(sd, p + f"attn.proj_out.{key}.bias")
                 W[f"{i}.{s}.nq"] = self._f(sd, p + f"attn.norm_q.{key}.weight")
                 W[f"{i}.{s}.nk"] = self._f(sd, p + f"attn.norm_k.{key}.weight")
+                W[f"{i}.{s}.nqk"] = torch.cat([W[f"{i}.{s}.nq"], W[f"{i}.{s}.nk"]]).contiguous()   # [2][128]
                 if last and s == "txt":
                     continue
                 if cfg["mlp"] == "swiglu":
@@ -344,15 +361,27 @@ class B200NaDiT(EngineModule):
             # ---- attention branch
             a_v = lib.rmsnorm_ada(x, m("vid.attn_scale"), m("vid.attn_shift"), mode=0, eps=cfg["eps"])
             a_t = lib.rmsnorm_ada(t, m("txt.attn_scale"), m("txt.attn_shift"), mode=0, eps=cfg["eps"])
-            qkv_v = lib.linear(a_v, k("vid", "qkv.w"))
             qkv_t = lib.linear(a_t, k("txt", "qkv.w"))
-            del a_v
             q, kk, v = qb[: lay.total], kb[: lay.total], vb[: lay.total]
-            lib.call("svr2_qk_norm_rope_window_bf16", lib.ptr(qkv_v), lib.ptr(qkv_t), lib.ptr(lay.row_src),
-                     lib.ptr(lay.row_rope), lib.ptr(cos_t), lib.ptr(sin_t), nfreq, lib.ptr(k("vid", "nq")),
-                     lib.ptr(k("vid", "nk")), lib.ptr(k("txt", "nq")), lib.ptr(k("txt", "nk")), cfg["eps"],
-                     lay.total, heads, lib.ptr(q), lib.ptr(kk), lib.ptr(v), st, nbytes=12.0 * lay.total * inner)
-            del qkv_v
+            rope_args = (lib.ptr(cos_t), lib.ptr(sin_t), nfreq)
+            if self.fuse_qkv:
+                # video rows: q/k RMSNorm + RoPE + window scatter inside the QKV GEMM's epilogue; text rows (the same
+                # 58 rows appended to every window) by the row-subset form of the stand-alone kernel
+                lib.call("svr2_linear_qkv_rope_bf16", lib.ptr(a_v), a_v.stride(0), lib.ptr(k("vid", "qkv.w")), d, L, heads, d,
+                         lib.ptr(lay.tok_dst), lib.ptr(lay.tok_rope), *rope_args, lib.ptr(k("vid", "nqk")), cfg["eps"],
+                         lib.ptr(q), lib.ptr(kk), lib.ptr(v), st, flops=2.0 * L * 3 * inner * d)
+                lib.call("svr2_qk_norm_rope_rows_bf16", None, lib.ptr(qkv_t), lib.ptr(lay.row_src), lib.ptr(lay.row_rope),
+                         *rope_args, lib.ptr(k("vid", "nq")), lib.ptr(k("vid", "nk")), lib.ptr(k("txt", "nq")),
+                         lib.ptr(k("txt", "nk")), cfg["eps"], lib.ptr(lay.txt_rows), lay.txt_rows.numel(), heads,
+                         lib.ptr(q), lib.ptr(kk), lib.ptr(v), st, nbytes=12.0 * lay.txt_rows.numel() * inner)
+            else:
+                qkv_v = lib.linear(a_v, k("vid", "qkv.w"))
+                lib.call("svr2_qk_norm_rope_window_bf16", lib.ptr(qkv_v), lib.ptr(qkv_t), lib.ptr(lay.row_src),
+                         lib.ptr(lay.row_rope), *rope_args, lib.ptr(k("vid", "nq")),
+                         lib.ptr(k("vid", "nk")), lib.ptr(k("txt", "nq")), lib.ptr(k("txt", "nk")), cfg["eps"],
+                         lay.total, heads, lib.ptr(q), lib.ptr(kk), lib.ptr(v), st, nbytes=12.0 * lay.total * inner)
+                del qkv_v
+            del a_v
             o_view = o_all.view(-1, heads, 128)
             self.attention.run(q, kk, v, lay.cu_seqlens, lay.max_len, out=o_view, out_row_map=lay.out_row_map,
                                flops=lay.attn_flops * heads)

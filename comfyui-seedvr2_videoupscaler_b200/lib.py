@@ -37,6 +37,10 @@ SIGNATURES = {
     "svr2_rmsnorm_ada_bf16": [_P, _P, c_int, c_int, c_float, _P, _P, _P, c_int, _P],
     "svr2_qk_norm_rope_window_bf16": [_P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_float, c_int, c_int, _P, _P,
                                       _P, _P],
+    "svr2_qk_norm_rope_rows_bf16": [_P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_float, _P, c_int, c_int, _P, _P,
+                                    _P, _P],
+    "svr2_linear_qkv_rope_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, c_float, _P,
+                                  _P, _P, _P],
     "svr2_txt_window_mean_bf16": [_P, _P, c_int, c_int, c_int, _P],
     "svr2_patchify_bf16": [_P, _P, c_int, c_int, c_int, c_int, c_int, _P],
     "svr2_unpatchify_bf16": [_P, c_int, _P, c_int, c_int, c_int, c_int, _P],

@@ -112,6 +112,20 @@ int svr2_qk_norm_rope_window_bf16(const void* qkv_vid, const void* qkv_txt, cons
                                   const int32_t* row_rope, const float* cos_tab, const float* sin_tab, int nfreq,
                                   const float* wq_vid, const float* wk_vid, const float* wq_txt, const float* wk_txt,
                                   float eps, int total, int heads, void* q, void* k, void* v, void* stream);
+/* the same kernel on the subset of output rows in row_list[n_rows] (window-order row ids) */
+int svr2_qk_norm_rope_rows_bf16(const void* qkv_vid, const void* qkv_txt, const int32_t* row_src, const int32_t* row_rope,
+                                const float* cos_tab, const float* sin_tab, int nfreq, const float* wq_vid,
+                                const float* wk_vid, const float* wq_txt, const float* wk_txt, float eps,
+                                const int32_t* row_list, int n_rows, int heads, void* q, void* k, void* v, void* stream);
+/* QKV projection (nn.Linear, mmattn.py:173) with everything NaSwinAttention does before the attention call fused into the
+ * GEMM epilogue: bf16 rounding of the projection, per-head q/k RMSNorm (fp32, affine [128]), 3-axis RoPE on interleaved
+ * pairs from cos/sin tables [R, nfreq] (nfreq = 21: 3B, 10: 7B), window partition (mmattn.py:199-248, rope.py:116-176).
+ * a [M, K] (row stride lda), w [3*heads*128, K]; token m goes to row tok_dst[m] of q / k / v ([rows, heads*128]);
+ * tok_rope [M, 3] = table rows per axis or -1; qk_weight [2][128] = q-norm, k-norm weights (fp32).  heads even. */
+int svr2_linear_qkv_rope_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int heads, int K,
+                              const int32_t* tok_dst, const int32_t* tok_rope, const float* cos_tab, const float* sin_tab,
+                              int nfreq, const float* qk_weight, float eps, void* q, void* k, void* v, void* stream);
+
 
 /* mean over windows of the text rows (na.py:396-417): in [n_win, l, dim] -> out [l, dim] */
 int svr2_txt_window_mean_bf16(const void* in, void* out, int n_win, int l, int dim, void* stream);

@@ -263,6 +263,49 @@ def test_qk_norm_rope_window(svr2lib):
     assert torch.equal(v.float(), rows[:, 2])
 
 
+@pytest.mark.parametrize("variant,heads,geom", [("3b", 2, (3, 20, 36)), ("3b", 4, (5, 34, 60)), ("7b", 2, (2, 20, 36)),
+                                                ("3b", 20, (1, 10, 14))])
+def test_linear_qkv_rope_fused_vs_unfused(pkg, svr2lib, variant, heads, geom):
+    """QKV GEMM with q/k RMSNorm + RoPE + window scatter in its epilogue (svr2_linear_qkv_rope_bf16) + the row-subset
+    kernel for the text rows, against the two-kernel path (svr2_linear_bf16 -> svr2_qk_norm_rope_window_bf16) on the real
+    window layouts (regular and shifted): v bit-equal, q/k equal up to the summation order of the per-head RMS."""
+    import importlib
+    dit = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.dit")
+    T, Hp, Wp = geom
+    l, d, inner = 58, heads * 128, heads * 128
+    L = T * Hp * Wp
+    a_v, a_t = bf(rnd(L, d, seed=1)), bf(rnd(l, d, seed=2))
+    w_v, w_t = bf(rnd(3 * inner, d, std=d ** -0.5, seed=3)), bf(rnd(3 * inner, d, std=d ** -0.5, seed=4))
+    nq_v, nk_v, nq_t, nk_t = (rnd(128, seed=s) * 0.1 + 1 for s in (5, 6, 7, 8))
+    nqk = torch.cat([nq_v, nk_v]).contiguous()
+    if variant == "3b":
+        freqs = (1.0 / (10000 ** (torch.arange(0, 42, 2)[:21].float() / 42))).half()
+    else:
+        freqs = (torch.linspace(1.0, 128.0, 10) * math.pi).half()
+    for shifted in (False, True):
+        lay, size_rows = dit.build_layout(T, Hp, Wp, l, shifted, variant, DEV)
+        c, s = dit.rope_tables(freqs, variant, int(lay.row_rope.max().item()) + 1, size_rows)
+        cos_t, sin_t = c.to(DEV), s.to(DEV)
+        nf = cos_t.shape[1]
+        P = svr2lib.ptr
+        qkv_v, qkv_t = svr2lib.linear(a_v, w_v), svr2lib.linear(a_t, w_t)
+        ref = [torch.zeros(lay.total, heads, 128, device=DEV, dtype=torch.bfloat16) for _ in range(3)]
+        svr2lib.call("svr2_qk_norm_rope_window_bf16", P(qkv_v), P(qkv_t), P(lay.row_src), P(lay.row_rope), P(cos_t),
+                     P(sin_t), nf, P(nq_v), P(nk_v), P(nq_t), P(nk_t), 1e-5, lay.total, heads, *(P(t) for t in ref),
+                     svr2lib.stream())
+        got = [torch.zeros_like(t) for t in ref]
+        svr2lib.call("svr2_linear_qkv_rope_bf16", P(a_v), d, P(w_v), d, L, heads, d, P(lay.tok_dst), P(lay.tok_rope),
+                     P(cos_t), P(sin_t), nf, P(nqk), 1e-5, *(P(t) for t in got), svr2lib.stream())
+        svr2lib.call("svr2_qk_norm_rope_rows_bf16", None, P(qkv_t), P(lay.row_src), P(lay.row_rope), P(cos_t), P(sin_t),
+                     nf, P(nq_v), P(nk_v), P(nq_t), P(nk_t), 1e-5, P(lay.txt_rows), lay.txt_rows.numel(), heads,
+                     *(P(t) for t in got), svr2lib.stream())
+        assert torch.equal(got[2], ref[2]), "v rows must be bit-equal"
+        for name, g_, r_ in (("q", got[0], ref[0]), ("k", got[1], ref[1])):
+            dlt = (g_.float() - r_.float()).abs()
+            assert (dlt == 0).float().mean() > 0.98 and dlt.max() <= 2 ** -6 * r_.abs().max().item(), \
+                f"{name} shifted={shifted}: {(dlt == 0).float().mean():.4f} equal, max {dlt.max():.4f}"
+
+
 @pytest.mark.parametrize("C,hw,frames,silu", [(128, 24 * 36, 3, 1), (256, 1000, 2, 1), (512, 77, 2, 0),
                                               (128, 300 * 200, 2, 1), (512, 20000, 1, 1)])
 def test_groupnorm(svr2lib, C, hw, frames, silu):
