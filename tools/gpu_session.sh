@@ -1,0 +1,19 @@
+#!/bin/bash
+# One GPU-box session of round 2: everything is logged under gpurun_out/ (merged back by gpurun).
+# usage (on the box, from the repo root): bash tools/gpu_session.sh [stage ...]   (default: all stages)
+set -u
+mkdir -p gpurun_out
+STAGES="${*:-tests glb detail ncu_attn bench}"
+for s in $STAGES; do
+  echo "=== stage $s $(date +%T)"
+  case $s in
+    tests)    timeout 900 python -m pytest tests -m gpu -q --durations=25 > gpurun_out/r2_pytest.log 2>&1; tail -45 gpurun_out/r2_pytest.log ;;
+    glb)      timeout 600 python tools/gpu_library_baseline.py --ops --phases cfg2,4k_shard --out gpurun_out/r2_gpu_library_baseline.json > gpurun_out/r2_glb.log 2>&1; tail -3 gpurun_out/r2_glb.log ;;
+    detail)   timeout 600 python bench.py --steps 3 --warmup 2 --phases --detail --no-cpu-baseline --lib-baseline none > gpurun_out/r2_bench_4k_detail.json 2> gpurun_out/r2_bench_4k_detail.txt; head -40 gpurun_out/r2_bench_4k_detail.txt ;;
+    ncu_attn) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_varlen -c 1 -f -o gpurun_out/r2_attn python tools/perf_conv_one.py attn > gpurun_out/r2_ncu_attn.log 2>&1; tail -3 gpurun_out/r2_ncu_attn.log ;;
+    bench)    timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r2_bench_4k.json 2> gpurun_out/r2_bench_4k.err; cut -c1-1500 gpurun_out/r2_bench_4k.json ;;
+    bench1080) timeout 600 python bench.py --workload 1080p --steps 5 --warmup 3 --phases --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_1080p.json 2> gpurun_out/r2_bench_1080p_phases.txt; cut -c1-600 gpurun_out/r2_bench_1080p.json ;;
+    *) echo "unknown stage $s" ;;
+  esac
+done
+echo "=== done $(date +%T)"
