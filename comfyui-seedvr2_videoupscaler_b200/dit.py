@@ -192,10 +192,52 @@ class B200NaDiT(EngineModule):
         # the fused QKV epilogue needs 256-column tiles to be whole head pairs and one of the two shipped RoPE widths
         self.fuse_qkv = (cfg["heads"] % 2 == 0 and os.environ.get("SVR2_FUSE_QKV", "1") != "0"
                          and self.rope_freqs[0].numel() in (21, 10))
+        # forward sequenced by the native runtime (default) or by this module's Python loop (per-call profiling, A/B)
+        self.native = os.environ.get("SVR2_NATIVE_DIT", "1") != "0"
 
     def _device_state_moved(self):
         if hasattr(self, "_layouts"):
             self._layouts.clear()      # window / RoPE tables live on the old device
+        self._drop_handle()
+
+    # ---- native runtime (csrc/engine.cu): the same forward sequenced in C++ on a svr2_t handle ---------------
+    def _drop_handle(self):
+        h = self.__dict__.get("_handle")
+        if h:
+            lib.engine_destroy(h)
+        self.__dict__["_handle"] = None
+
+    def __del__(self):
+        try:
+            self._drop_handle()
+        except Exception:   # noqa: BLE001 - interpreter shutdown
+            pass
+
+    def native_handle(self):
+        """svr2_t* that borrows this module's weight buffers (they stay under nn.Module lifecycle control) and owns
+        its workspace; rebuilt after a device move."""
+        if self.__dict__.get("_handle"):
+            return self._handle
+        cfg = self.cfg
+        mlp_hidden = (self.W["0.vid.mlp_in.w"].shape[0] // 2) if cfg["mlp"] == "swiglu" else self.W["0.vid.mlp_in.w"].shape[0]
+        desc = lib.ModelDesc(variant=0 if cfg["variant"] == "3b" else 1, dim=cfg["dim"], heads=cfg["heads"],
+                             layers=cfg["layers"], mm_layers=cfg["mm_layers"], txt_in_dim=cfg["txt_in_dim"],
+                             in_ch=cfg["in_ch"], out_ch=cfg["out_ch"], mlp_kind=0 if cfg["mlp"] == "swiglu" else 1,
+                             mlp_hidden=mlp_hidden, out_norm=int(cfg["out_norm"]), last_vid_only=int(cfg["last_vid_only"]),
+                             eps=cfg["eps"], timestep=self.timestep)
+        h = lib.engine_create(desc, self.device.index if self.device.index is not None else torch.cuda.current_device())
+        try:
+            lib.engine_load(h, {k: self.W[k] for k in self.W.keys()}, copy=False)
+            lib.engine_load(h, {k: self.M[k] for k in self.M.keys()}, copy=False)
+            lib.engine_load(h, {f"{i}.rope_freqs": f for i, f in enumerate(self.rope_freqs)}, copy=True)
+        except Exception:
+            lib.engine_destroy(h)
+            raise
+        self.__dict__["_handle"] = h
+        return h
+
+    def workspace_bytes(self, T: int, H: int, W: int, txt_len: int = 58) -> int:
+        return int(lib.load().svr2_workspace_bytes(self.native_handle(), T, H, W, txt_len))
 
     # ---- weights ---------------------------------------------------------
     def _w(self, sd, key):
@@ -334,6 +376,13 @@ class B200NaDiT(EngineModule):
         L = T * Hp * Wp
         vid = vid.to(dev, torch.bfloat16).contiguous()
         txt = txt.to(dev, torch.bfloat16).contiguous()
+        if self.native and lib.PROFILER is None and self.fuse_qkv == (cfg["heads"] % 2 == 0):
+            out = torch.empty(T * H * Wd, cfg["out_ch"], device=dev, dtype=torch.bfloat16)
+            lib.call("svr2_dit_forward", self.native_handle(), lib.ptr(vid), lib.ptr(txt), T, H, Wd, l, lib.ptr(out),
+                     lib.stream())
+            n_l = cfg["layers"]
+            lib.LAUNCHES += 15 * n_l - (3 if cfg["last_vid_only"] else 0) + 5 + (1 if cfg["out_norm"] else 0) - 1
+            return NaDiTOutput(out)
         layouts, tables = self._geometry(T, Hp, Wp, l)
         st = lib.stream()
 

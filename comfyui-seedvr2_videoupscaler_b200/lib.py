@@ -17,12 +17,29 @@ LIB_PATH = os.path.join(HERE, "csrc", "libsvr2.so")
 EPI_BIAS, EPI_GATE, EPI_RESIDUAL, EPI_SWIGLU, EPI_GELU, EPI_F32, EPI_SILU = 1, 2, 4, 8, 16, 32, 128
 EPI_ROWSTAT, EPI_PEXP = 256, 512
 
+class ModelDesc(ctypes.Structure):
+    """svr2_model_desc (include/svr2.h)"""
+    _fields_ = [("variant", c_int), ("dim", c_int), ("heads", c_int), ("layers", c_int), ("mm_layers", c_int),
+                ("txt_in_dim", c_int), ("in_ch", c_int), ("out_ch", c_int), ("mlp_kind", c_int), ("mlp_hidden", c_int),
+                ("out_norm", c_int), ("last_vid_only", c_int), ("eps", c_float), ("timestep", c_float)]
+
+
+class TensorDesc(ctypes.Structure):
+    """svr2_tensor_desc (include/svr2.h)"""
+    _fields_ = [("name", ctypes.c_char_p), ("data", c_void_p), ("dtype", c_int), ("rank", c_int), ("shape", c_int64 * 5)]
+
+
 # name -> argtypes; every function returns int (svr2_status) except svr2_last_error
 _P = c_void_p
 SIGNATURES = {
     "svr2_version": [],
     "svr2_set_cta_pair": [c_int],
     "svr2_device_check": [POINTER(c_int), POINTER(c_int), POINTER(c_int)],
+    "svr2_create": [POINTER(c_void_p), c_int, POINTER(ModelDesc)],
+    "svr2_destroy": [_P],
+    "svr2_load_weights": [_P, POINTER(TensorDesc), ctypes.c_size_t, c_int],
+    "svr2_workspace_bytes": [_P, c_int, c_int, c_int, c_int],
+    "svr2_dit_forward": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
     "svr2_linear_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, c_float, _P],
     "svr2_conv3d_bf16": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_int, _P, _P, _P, c_int, c_int, c_int, _P],
@@ -86,9 +103,11 @@ def load() -> ctypes.CDLL:
         lib = ctypes.CDLL(LIB_PATH)
         lib.svr2_last_error.restype = ctypes.c_char_p
         lib.svr2_last_error.argtypes = []
+        lib.svr2_engine_last_error.restype = ctypes.c_char_p
+        lib.svr2_engine_last_error.argtypes = [c_void_p]
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
-            fn.restype = c_int64 if name.endswith("_bytes") else (None if name == "svr2_set_cta_pair" else c_int)
+            fn.restype = c_int64 if name.endswith("_bytes") else (None if name in ("svr2_set_cta_pair", "svr2_destroy") else c_int)
             fn.argtypes = args
         _lib = lib
     return _lib
@@ -230,3 +249,33 @@ def conv3d(x, T_in_total, H, W, Cin, w, Cout, k, stride_t, stride_hw, pad_hw, T_
          int(ldc if ldc is not None else Cout), stream(),
          flops=2.0 * T_out * (H // stride_hw) * (W // stride_hw) * Cout * k[0] * k[1] * k[2] * Cin)
     return y
+
+
+# --------------------------------------------------------------------------
+# handle API (native host runtime, csrc/engine.cu)
+# --------------------------------------------------------------------------
+_TORCH_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def engine_create(desc: ModelDesc, device_index: int) -> c_void_p:
+    h = c_void_p()
+    _check(load().svr2_create(ctypes.byref(h), int(device_index), ctypes.byref(desc)), "svr2_create")
+    return h
+
+
+def engine_load(handle: c_void_p, tensors: dict, copy: bool) -> None:
+    """tensors: engine-layout name -> torch tensor (CUDA tensors are borrowed when copy is False; host tensors need copy)."""
+    items = [(k, t.contiguous()) for k, t in tensors.items()]
+    arr = (TensorDesc * len(items))()
+    for d, (k, t) in zip(arr, items):
+        d.name, d.data, d.dtype, d.rank = k.encode(), t.data_ptr(), _TORCH_DT[t.dtype], max(t.ndim, 1)
+        for i, n in enumerate(t.shape if t.ndim else (1,)):
+            d.shape[i] = n
+    _check(load().svr2_load_weights(handle, arr, len(items), int(copy)), "svr2_load_weights")
+    if copy:
+        torch.cuda.synchronize()          # the sources may be temporaries
+
+
+def engine_destroy(handle) -> None:
+    if handle:
+        load().svr2_destroy(handle)

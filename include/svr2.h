@@ -13,6 +13,7 @@
  */
 #ifndef SVR2_H_
 #define SVR2_H_
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -47,6 +48,48 @@ void svr2_set_cta_pair(int on);
 int svr2_version(void);
 /* fills sm count / major / minor of the current device; SVR2_ERR_ARCH unless sm_100 */
 int svr2_device_check(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- Handle-based engine API: one svr2_t per (process, device); not thread-safe; all work is
+ * stream-ordered on the passed stream.  Ownership: the caller owns every I/O buffer; the engine owns its workspace and
+ * the weights it copied (or borrows device pointers that must outlive the handle).  Errors: 0 = ok, negative svr2_status,
+ * message from svr2_engine_last_error(); nothing throws across the ABI; there is no CPU fallback.
+ *
+ * The handle runs the whole NaDiT forward natively (C++ host runtime, csrc/engine.cu): window / RoPE geometry
+ * (window.py:28-83, na.py:320-424,583-641, rope.py:130-176), workspace plan and the kernel sequence of
+ * NaDiT.forward (dit_3b/nadit.py:190-248, dit_7b/nadit.py:152-190) for b = 1 at the folded timestep. */
+typedef struct svr2_engine svr2_t;
+typedef struct svr2_model_desc {
+  int variant;        /* 0 = SeedVR2-3B structure, 1 = 7B structure (RoPE kind, window-size tables) */
+  int dim, heads;     /* dim == heads * 128 */
+  int layers, mm_layers;
+  int txt_in_dim, in_ch, out_ch;
+  int mlp_kind;       /* 0 = SwiGLU (mlp.py:46-62), 1 = GELU-tanh with biases (dit_7b/mlp.py:28-43) */
+  int mlp_hidden;     /* 6912 (3B) / 12288 (7B) */
+  int out_norm;       /* vid_out_norm + vid_out_ada present (3B) */
+  int last_vid_only;  /* last block: text stream skips ada / mlp (mmsr_block.py:73-82) */
+  float eps;
+  float timestep;     /* the t folded into the AdaSingle vectors at load (informational) */
+} svr2_model_desc;
+typedef struct svr2_tensor_desc {
+  const char* name;   /* engine-layout name, e.g. "12.vid.qkv.w", "12.vid.attn_scale", "12.rope_freqs", "vid_in.w" */
+  const void* data;   /* host or device pointer */
+  int dtype;          /* 0 fp32, 1 bf16, 2 fp16 */
+  int rank;
+  int64_t shape[5];
+} svr2_tensor_desc;
+int svr2_create(svr2_t** out, int device, const svr2_model_desc* desc);
+void svr2_destroy(svr2_t* engine);
+const char* svr2_engine_last_error(svr2_t* engine);
+/* Weights in the engine layout (what weights.py / B200NaDiT._load produce: K-major bf16 matrices, SwiGLU gate / in rows
+ * interleaved per 128, AdaSingle vectors E[:,layer,g] + P folded to fp32, "<i>.rope_freqs" in the checkpoint dtype).
+ * copy != 0: the engine copies (caller keeps ownership of the source); copy == 0: device pointers are borrowed. */
+int svr2_load_weights(svr2_t* engine, const svr2_tensor_desc* tensors, size_t n, int copy);
+/* bytes of engine-owned workspace one forward of this geometry uses (T, H, W = latent frames / rows / columns) */
+size_t svr2_workspace_bytes(svr2_t* engine, int T, int H, int W, int txt_len);
+/* vid [T*H*W, in_ch] bf16, txt [txt_len, txt_in_dim] bf16 -> out [T*H*W, out_ch] bf16 (NaDiTOutput.vid_sample).  The
+ * first call for a geometry builds its index tables (synchronous uploads) and may grow the workspace. */
+int svr2_dit_forward(svr2_t* engine, const void* vid, const void* txt, int T, int H, int W, int txt_len, void* out,
+                     void* stream);
 
 /* ---- K1: Linear.  out[M,N] = epi(a[M,K] @ w[N,K]^T).  Replaces nn.Linear at
  * dit_3b/nablocks/attention/mmattn.py:56-59,173,269; dit_3b/mlp.py:56-61; dit_7b/mlp.py:35-43;

@@ -21,9 +21,28 @@ def test_library_exports_every_declared_symbol(svr2lib):
     lib = svr2lib.load()
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/svr2.h but not exported"
-    assert set(svr2lib.SIGNATURES) | {"svr2_last_error"} == declared
+    assert set(svr2lib.SIGNATURES) | {"svr2_last_error", "svr2_engine_last_error"} == declared
     assert lib.svr2_version() >= 100
     assert isinstance(lib.svr2_last_error(), bytes)
+
+
+def test_handle_api_fails_loudly_without_a_gpu(svr2lib):
+    """svr2_create on a box without a B200 returns a status (never a usable handle, never a fallback); argument checks
+    of the handle API work without a device."""
+    import ctypes
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    lib = svr2lib.load()
+    desc = svr2lib.ModelDesc(variant=0, dim=256, heads=2, layers=2, mm_layers=1, txt_in_dim=64, in_ch=33, out_ch=16,
+                             mlp_kind=0, mlp_hidden=768, out_norm=1, last_vid_only=1, eps=1e-5, timestep=1000.0)
+    h = ctypes.c_void_p()
+    assert lib.svr2_create(ctypes.byref(h), 0, ctypes.byref(desc)) < 0 and not h.value
+    assert lib.svr2_last_error()
+    bad = svr2lib.ModelDesc(variant=0, dim=300, heads=2)
+    assert lib.svr2_create(ctypes.byref(h), 0, ctypes.byref(bad)) == -1          # SVR2_ERR_ARG: dim != heads * 128
+    assert lib.svr2_workspace_bytes(None, 3, 20, 36, 58) == 0
+    with pytest.raises(svr2lib.Svr2Error):
+        svr2lib.engine_create(desc, 0)
 
 
 def test_product_path_has_no_oracle_or_fallback():

@@ -272,3 +272,29 @@ def test_vae_tiled_vs_reference_golden_and_oracle(vae_pair):
         d = (out.float() - seam.float()).abs()
         assert (d == 0).float().mean() > 0.99 and d.max() <= 2 ** -6 * max(1.0, seam.abs().max().item()), \
             f"{name}: seam arithmetic differs from the reference's op order ({(d == 0).float().mean():.4f} equal, max {d.max():.4f})"
+
+
+@pytest.mark.parametrize("name", ["dit3b_tiny_t3", "dit7b_tiny_t3"])
+def test_dit_native_runtime_equals_python_sequencing(pkg, name):
+    """svr2_dit_forward (C++ host runtime on a svr2_t handle: geometry, workspace plan, kernel sequence) against the
+    same forward sequenced by the Python module: same kernels in the same order -> bit-identical output; the handle
+    reports its workspace size and survives a second geometry."""
+    dit = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.dit")
+    variant, over, (T, H, W), l = DIT_CASES[name]
+    cfg = dit.dit_config(variant, **over)
+    sd = pkg.weights.synth_dit_state_dict(cfg, seed=1234, dtype=torch.float16)
+    vid, txt = dit_inputs(cfg, T, H, W, l)
+    eng = dit.B200NaDiT(cfg, sd)
+    eng.native = True
+    out_n = eng(vid.cuda(), txt.cuda(), [[T, H, W]], [[l]]).vid_sample.clone()
+    eng.native = False
+    out_p = eng(vid.cuda(), txt.cuda(), [[T, H, W]], [[l]]).vid_sample
+    assert torch.equal(out_n, out_p), f"{name}: native vs python sequencing {psnr(out_n, out_p):.1f} dB"
+    assert eng.workspace_bytes(T, H, W, l) > 0
+    eng.native = True
+    g = torch.Generator().manual_seed(9)
+    vid2 = torch.randn(1 * 16 * 24, cfg["in_ch"], generator=g)
+    o2 = eng(vid2.cuda(), txt.cuda(), [[1, 16, 24]], [[l]]).vid_sample
+    eng.native = False
+    assert torch.equal(o2, eng(vid2.cuda(), txt.cuda(), [[1, 16, 24]], [[l]]).vid_sample)
+    assert torch.equal(out_n, dit.B200NaDiT(cfg, sd)(vid.cuda(), txt.cuda(), [[T, H, W]], [[l]]).vid_sample)
