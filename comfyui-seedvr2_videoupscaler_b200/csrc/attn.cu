@@ -57,21 +57,20 @@ struct AttnParams {
   __nv_bfloat16* out;
   int heads;
   float scale_log2;  // softmax_scale * log2(e)
+  int n_qt;          // q tiles per sequence (of the longest sequence)
+  int n_work;        // n_qt * n_seq * heads work items
 };
 
-// Software pipeline inside a CTA: S_{j+1} = Q K_{j+1}^T is issued as soon as the softmax warps have pulled S_j
-// into registers, so the tensor pipe computes the next scores while tile j is in its softmax, and P_j V_j runs
-// while tile j+1 is in its softmax.  K is double-buffered (loaded two tiles ahead), V single-buffered; the
-// second CTA on the SM (~98 KB smem each) fills the remaining bubbles.
+// Persistent CTAs (two per SM): every CTA walks the work list (q-tile, sequence, head) with a fixed stride, so barrier
+// setup, the TMEM allocation and — above all — the TMA round trip for Q and the first K tiles are paid once per CTA
+// instead of once per 128 query rows: the producer warp runs ahead into the next work item while the softmax warps
+// finish the current one, and the first S = Q K^T of the next item is issued as soon as the score buffer is free.
+// Inside an item the software pipeline is the same as before: S_{j+1} = Q K_{j+1}^T is issued as soon as the softmax
+// warps have pulled S_j into registers, P_j V_j runs while tile j+1 is in its softmax; K is double-buffered, V single.
+// All barrier phases are tracked with running counters (tiles / items processed by this CTA).
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  const int seq = blockIdx.y, head = blockIdx.z, qt = blockIdx.x;
-  const int s_begin = p.cu_seqlens[seq], s_end = p.cu_seqlens[seq + 1];
-  const int len = s_end - s_begin;
-  if (qt * ATT_BM >= len) return;
-  const int n_kv = (len + ATT_BN - 1) / ATT_BN;
-
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::kBar);
@@ -86,7 +85,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* pv_done = bars + 8;
   uint64_t* k_full1 = bars + 9;                    // second K stage
   uint64_t* k_empty1 = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* q_empty = bars + 11;                   // all Q K^T of an item issued and retired: Q may be overwritten
+  uint64_t* o_free = bars + 12;                    // the epilogue has read O: the next item's P V may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -104,6 +105,8 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     mbar_init(s_free, 128);
     mbar_init(p_ready, 128);
     mbar_init(pv_done, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);     // S: 64 columns, O: 128 columns
@@ -113,34 +116,55 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
 
-  const int col0 = head * ATT_D;
-  const int q_row0 = s_begin + qt * ATT_BM;
+  // work item w -> (q tile, head, sequence); q tiles of one (sequence, head) are neighbours so that the CTAs running
+  // at the same time share its K / V through L2
+  const int n_qt = p.n_qt, n_work = p.n_work;
+  auto decode = [&](int w, int& qt, int& head, int& s_begin, int& len) {
+    qt = w % n_qt;
+    const int rest = w / n_qt;
+    head = rest % p.heads;
+    const int seq = rest / p.heads;
+    s_begin = p.cu_seqlens[seq];
+    len = p.cu_seqlens[seq + 1] - s_begin;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_Q_BYTES);
-      tma_load_2d(smem + AttnSmem::kQ, &tmap_q, q_full, col0, q_row0);
-      tma_load_2d(smem + AttnSmem::kQ + ATT_QH_BYTES, &tmap_q, q_full, col0 + 64, q_row0);
-      auto load_k = [&](int j) {                   // K_j -> stage j & 1 (its previous tenant was K_{j-2})
-        const int st = j & 1;
-        uint64_t* full = st ? k_full1 : k_full;
-        uint64_t* empty = st ? k_empty1 : k_empty;
-        uint8_t* dst = smem + (st ? AttnSmem::kK1 : AttnSmem::kK);
-        const int r0 = s_begin + j * ATT_BN;
-        mbar_wait(empty, ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(full, ATT_KV_BYTES);
-        tma_load_2d(dst, &tmap_k, full, col0, r0);
-        tma_load_2d(dst + ATT_KVH_BYTES, &tmap_k, full, col0 + 64, r0);
-      };
-      load_k(0);
-      if (n_kv > 1) load_k(1);
-      for (int j = 0; j < n_kv; ++j) {
-        const int r0 = s_begin + j * ATT_BN;
-        mbar_wait(v_empty, (j & 1) ^ 1);
-        mbar_expect_tx(v_full, ATT_KV_BYTES);
-        tma_load_2d(smem + AttnSmem::kV, &tmap_v, v_full, col0, r0);
-        tma_load_2d(smem + AttnSmem::kV + ATT_KVH_BYTES, &tmap_v, v_full, col0 + 64, r0);
-        if (j + 2 < n_kv) load_k(j + 2);           // waits for Q K_j^T to retire
+      uint32_t it = 0, kq = 0, vq = 0;             // items, K tiles, V tiles loaded so far
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        int qt, head, s_begin, len;
+        decode(w, qt, head, s_begin, len);
+        if (qt * ATT_BM >= len) continue;
+        const int n_kv = (len + ATT_BN - 1) / ATT_BN;
+        const int col0 = head * ATT_D, q_row0 = s_begin + qt * ATT_BM;
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, ATT_Q_BYTES);
+        tma_load_2d(smem + AttnSmem::kQ, &tmap_q, q_full, col0, q_row0);
+        tma_load_2d(smem + AttnSmem::kQ + ATT_QH_BYTES, &tmap_q, q_full, col0 + 64, q_row0);
+        auto load_k = [&](int j) {                 // K_j -> stage kq & 1 (its previous tenant was the K tile two loads ago)
+          const int st = kq & 1;
+          uint64_t* full = st ? k_full1 : k_full;
+          uint64_t* empty = st ? k_empty1 : k_empty;
+          uint8_t* dst = smem + (st ? AttnSmem::kK1 : AttnSmem::kK);
+          const int r0 = s_begin + j * ATT_BN;
+          mbar_wait(empty, ((kq >> 1) & 1) ^ 1);
+          mbar_expect_tx(full, ATT_KV_BYTES);
+          tma_load_2d(dst, &tmap_k, full, col0, r0);
+          tma_load_2d(dst + ATT_KVH_BYTES, &tmap_k, full, col0 + 64, r0);
+          ++kq;
+        };
+        load_k(0);
+        if (n_kv > 1) load_k(1);
+        for (int j = 0; j < n_kv; ++j) {
+          const int r0 = s_begin + j * ATT_BN;
+          mbar_wait(v_empty, (vq & 1) ^ 1);
+          mbar_expect_tx(v_full, ATT_KV_BYTES);
+          tma_load_2d(smem + AttnSmem::kV, &tmap_v, v_full, col0, r0);
+          tma_load_2d(smem + AttnSmem::kV + ATT_KVH_BYTES, &tmap_v, v_full, col0 + 64, r0);
+          ++vq;
+          if (j + 2 < n_kv) load_k(j + 2);         // waits for Q K_j^T to retire
+        }
+        ++it;
       }
     }
   } else if (warp == 1) {
@@ -151,38 +175,50 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const uint32_t p_addr = smem_u32(smem + AttnSmem::kP);
       const uint32_t k_addr = smem_u32(smem + AttnSmem::kK);
       const uint32_t v_addr = smem_u32(smem + AttnSmem::kV);
-      auto issue_qk = [&](int j) {                 // S_j = Q K_j^T, K_j in stage j & 1
-        const int st = j & 1;
-        mbar_wait(st ? k_full1 : k_full, (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t kb = st ? smem_u32(smem + AttnSmem::kK1) : k_addr;
+      uint32_t it = 0, kc = 0, g = 0;              // items, K tiles consumed, S tiles produced (== tiles started)
+      uint32_t gp = 0;                             // P V products issued
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        int qt, head, s_begin, len;
+        decode(w, qt, head, s_begin, len);
+        if (qt * ATT_BM >= len) continue;
+        const int n_kv = (len + ATT_BN - 1) / ATT_BN;
+        auto issue_qk = [&](bool last) {           // next S = Q K^T into the (single) score buffer
+          if (g > 0) mbar_wait(s_free, (g - 1) & 1);       // the softmax warps hold the previous S in registers
+          const int st = kc & 1;
+          mbar_wait(st ? k_full1 : k_full, (kc >> 1) & 1);
+          tc_fence_after();
+          const uint32_t kb = st ? smem_u32(smem + AttnSmem::kK1) : k_addr;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {                 // contraction over d = 128
-          const uint64_t da = umma_desc_kmajor_sw128(q_addr + (kk >> 2) * ATT_QH_BYTES) + uint64_t((kk & 3) * 2);
-          const uint64_t db = umma_desc_kmajor_sw128(kb + (kk >> 2) * ATT_KVH_BYTES) + uint64_t((kk & 3) * 2);
-          umma_bf16(tmem_s, da, db, idesc_qk, kk != 0);
-        }
-        umma_commit(st ? k_empty1 : k_empty);            // this K stage may be refilled (with K_{j+2})
-        umma_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {
-          mbar_wait(s_free, j & 1);                      // the softmax warps hold S_j in registers
-          issue_qk(j + 1);                               // next scores while tile j is in its softmax
-        }
-        mbar_wait(v_full, j & 1);
-        mbar_wait(p_ready, j & 1);                       // P_j in smem, O rescaled
-        tc_fence_after();
+          for (int kk = 0; kk < 8; ++kk) {                 // contraction over d = 128
+            const uint64_t da = umma_desc_kmajor_sw128(q_addr + (kk >> 2) * ATT_QH_BYTES) + uint64_t((kk & 3) * 2);
+            const uint64_t db = umma_desc_kmajor_sw128(kb + (kk >> 2) * ATT_KVH_BYTES) + uint64_t((kk & 3) * 2);
+            umma_bf16(tmem_s, da, db, idesc_qk, kk != 0);
+          }
+          umma_commit(st ? k_empty1 : k_empty);            // this K stage may be refilled
+          if (last) umma_commit(q_empty);                  // and Q, by the next item
+          umma_commit(s_full);
+          ++kc;
+          ++g;
+        };
+        mbar_wait(q_full, it & 1);
+        issue_qk(n_kv == 1);
+        for (int j = 0; j < n_kv; ++j) {
+          if (j + 1 < n_kv) issue_qk(j + 2 == n_kv);       // next scores while tile j is in its softmax
+          mbar_wait(v_full, gp & 1);
+          mbar_wait(p_ready, gp & 1);                      // P_j in smem, O rescaled
+          if (j == 0) mbar_wait(o_free, (it & 1) ^ 1);     // the previous item's O has been read out
+          tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < ATT_BN / 16; ++kk) {       // contraction over the 64 kv rows (16 per MMA)
-          const uint64_t da = umma_desc_kmajor_sw128(p_addr) + uint64_t(kk * 2);
-          const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, ATT_KVH_BYTES, 1024);
-          umma_bf16(tmem_o, da, db, idesc_pv, (j | kk) != 0);
+          for (int kk = 0; kk < ATT_BN / 16; ++kk) {       // contraction over the 64 kv rows (16 per MMA)
+            const uint64_t da = umma_desc_kmajor_sw128(p_addr) + uint64_t(kk * 2);
+            const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, ATT_KVH_BYTES, 1024);
+            umma_bf16(tmem_o, da, db, idesc_pv, (j | kk) != 0);
+          }
+          umma_commit(v_empty);
+          umma_commit(pv_done);
+          ++gp;
         }
-        umma_commit(v_empty);
-        umma_commit(pv_done);
+        ++it;
       }
     }
   } else {
@@ -195,103 +231,113 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // in fp32 / bf16 (relative rounding), and the O rescale below (four TMEM round trips on the critical path) becomes
     // rare instead of happening on almost every early tile.
     constexpr float kGrow = 8.0f;
-    float m_ref = -INFINITY, l_run = 0.f;
     const float sc = p.scale_log2;
-    uint8_t* sp = smem + AttnSmem::kP;
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      uint32_t sv[ATT_BN];
-      tmem_ld32(tmem_s + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-      tmem_ld32(tmem_s + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_free);                      // S may be overwritten by the next QK^T
-      const int kv_valid = len - j * ATT_BN;    // columns >= kv_valid are padding / the next sequence
-      if (kv_valid < ATT_BN) {                  // only the last tile of a sequence is ragged
-#pragma unroll
-        for (int c = 0; c < ATT_BN; ++c)
-          if (c >= kv_valid) sv[c] = 0xff800000u;   // -inf
-      }
-      // row maximum: four independent chains of 3-input max
-      float mx4[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) mx4[a] = __uint_as_float(sv[a]);
-#pragma unroll
-      for (int c = 4; c < ATT_BN; c += 8) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          mx4[a] = fmaxf(fmaxf(mx4[a], __uint_as_float(sv[c + a])), __uint_as_float(sv[(c + 4 + a) & (ATT_BN - 1)]));
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const bool grow = (mx - m_ref) * sc > kGrow;                   // true on the first tile (m_ref = -inf)
-      const float m_new = grow ? mx : m_ref;
-      const float alpha = grow ? fast_exp2((m_ref - m_new) * sc) : 1.0f;   // 0 on the first tile
-      const float2 nmb = make_float2(-m_new * sc, -m_new * sc);
-      const float2 sc2 = make_float2(sc, sc);
-      // P = exp2(s * sc - m_new * sc): packed fp32x2 FMAs, four independent partial sums
-      float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-      uint32_t pk[ATT_BN / 2];
-#pragma unroll
-      for (int c = 0; c < ATT_BN; c += 2) {
-        const float2 t = ffma2(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sc2, nmb);
-        const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
-        ls[(c >> 1) & 1] = fadd2(ls[(c >> 1) & 1], e);
-        pk[c / 2] = pack_bf16x2(e.x, e.y);
-      }
-      const float lsum = (ls[0].x + ls[1].x) + (ls[0].y + ls[1].y);
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);        // P_{j-1} V_{j-1} has read the P buffer and updated O
+    const uint32_t sp_row = smem_u32(smem + AttnSmem::kP) + row * 128;
+    uint32_t g = 0;                            // tiles processed by this CTA (phase of s_full / s_free / p_ready / pv_done)
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      int qt, head, s_begin, len;
+      decode(w, qt, head, s_begin, len);
+      if (qt * ATT_BM >= len) continue;
+      const int n_kv = (len + ATT_BN - 1) / ATT_BN;
+      float m_ref = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++g) {
+        mbar_wait(s_full, g & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 64) {
-            uint32_t o[64];
-            tmem_ld32(tmem_o + lane_off + c0, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-            tmem_ld32(tmem_o + lane_off + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
-            tmem_ld_wait();
+        uint32_t sv[ATT_BN];
+        tmem_ld32(tmem_s + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_ld32(tmem_s + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_free);                      // S may be overwritten by the next QK^T
+        const int kv_valid = len - j * ATT_BN;    // columns >= kv_valid are padding / the next sequence
+        if (kv_valid < ATT_BN) {                  // only the last tile of a sequence is ragged
 #pragma unroll
-            for (int e = 0; e < 64; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-            tmem_st32(tmem_o + lane_off + c0, *reinterpret_cast<const uint32_t(*)[32]>(&o[0]));
-            tmem_st32(tmem_o + lane_off + c0 + 32, *reinterpret_cast<const uint32_t(*)[32]>(&o[32]));
-          }
-          tmem_st_wait();
+          for (int c = 0; c < ATT_BN; ++c)
+            if (c >= kv_valid) sv[c] = 0xff800000u;   // -inf
         }
-      }
-      // P -> swizzled K-major smem (row = this thread, 8 chunks of 16 B)
+        // row maximum: four independent chains of 3-input max
+        float mx4[4];
 #pragma unroll
-      for (int ch = 0; ch < ATT_BN / 8; ++ch) {
-        uint8_t* dst = sp + row * 128 + ((ch ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-      }
-      l_run = l_run * alpha + lsum;
-      m_ref = m_new;
-      fence_proxy_async_smem();                  // make P visible to the tensor core (async proxy)
-      tc_fence_before();
-      mbar_arrive(p_ready);
-    }
-    // ------------------------------ epilogue: O / l -> bf16 -> global
-    mbar_wait(pv_done, (n_kv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    const int q_idx = qt * ATT_BM + row;
-    const bool valid = q_idx < len;
-    long long grow = (long long)(s_begin + q_idx);
-    if (valid && p.out_row_map) grow = p.out_row_map[grow];
-    __nv_bfloat16* orow = p.out + (grow * p.heads + head) * ATT_D;
+        for (int a = 0; a < 4; ++a) mx4[a] = __uint_as_float(sv[a]);
+#pragma unroll
+        for (int c = 4; c < ATT_BN; c += 8) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            mx4[a] = fmaxf(fmaxf(mx4[a], __uint_as_float(sv[c + a])), __uint_as_float(sv[(c + 4 + a) & (ATT_BN - 1)]));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        const bool grow = (mx - m_ref) * sc > kGrow;                   // true on the first tile (m_ref = -inf)
+        const float m_new = grow ? mx : m_ref;
+        const float alpha = grow ? fast_exp2((m_ref - m_new) * sc) : 1.0f;   // 0 on the first tile
+        const float2 nmb = make_float2(-m_new * sc, -m_new * sc);
+        const float2 sc2 = make_float2(sc, sc);
+        // P = exp2(s * sc - m_new * sc): packed fp32x2 FMAs, four independent partial sums
+        float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        uint32_t pk[ATT_BN / 2];
+#pragma unroll
+        for (int c = 0; c < ATT_BN; c += 2) {
+          const float2 t = ffma2(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sc2, nmb);
+          const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+          ls[(c >> 1) & 1] = fadd2(ls[(c >> 1) & 1], e);
+          pk[c / 2] = pack_bf16x2(e.x, e.y);
+        }
+        const float lsum = (ls[0].x + ls[1].x) + (ls[0].y + ls[1].y);
+        if (j > 0) {
+          mbar_wait(pv_done, (g - 1) & 1);        // P_{j-1} V_{j-1} has read the P buffer and updated O
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
-      uint32_t o[32];
-      tmem_ld32(tmem_o + lane_off + c0, o);
-      tmem_ld_wait();
-      if (valid) {
+            for (int c0 = 0; c0 < 128; c0 += 64) {
+              uint32_t o[64];
+              tmem_ld32(tmem_o + lane_off + c0, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+              tmem_ld32(tmem_o + lane_off + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+              tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; e += 8) {
-          uint4 pk4 = make_uint4(pack_bf16x2(__uint_as_float(o[e]) * inv_l, __uint_as_float(o[e + 1]) * inv_l),
-                                 pack_bf16x2(__uint_as_float(o[e + 2]) * inv_l, __uint_as_float(o[e + 3]) * inv_l),
-                                 pack_bf16x2(__uint_as_float(o[e + 4]) * inv_l, __uint_as_float(o[e + 5]) * inv_l),
-                                 pack_bf16x2(__uint_as_float(o[e + 6]) * inv_l, __uint_as_float(o[e + 7]) * inv_l));
-          *reinterpret_cast<uint4*>(orow + c0 + e) = pk4;
+              for (int e = 0; e < 64; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st32(tmem_o + lane_off + c0, *reinterpret_cast<const uint32_t(*)[32]>(&o[0]));
+              tmem_st32(tmem_o + lane_off + c0 + 32, *reinterpret_cast<const uint32_t(*)[32]>(&o[32]));
+            }
+            tmem_st_wait();
+          }
+        }
+        // P -> swizzled K-major smem (row = this thread, 8 chunks of 16 B); explicit shared-space stores
+#pragma unroll
+        for (int ch = 0; ch < ATT_BN / 8; ++ch)
+          st_shared_v4(sp_row + ((ch ^ (row & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        l_run = l_run * alpha + lsum;
+        m_ref = m_new;
+        fence_proxy_async_smem();                  // make P visible to the tensor core (async proxy)
+        tc_fence_before();
+        mbar_arrive(p_ready);
+      }
+      // ------------------------------ epilogue: O / l -> bf16 -> global
+      mbar_wait(pv_done, (g - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      const int q_idx = qt * ATT_BM + row;
+      const bool valid = q_idx < len;
+      long long grow_ = (long long)(s_begin + q_idx);
+      if (valid && p.out_row_map) grow_ = p.out_row_map[grow_];
+      __nv_bfloat16* orow = p.out + (grow_ * p.heads + head) * ATT_D;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 64) {
+        uint32_t o[64];
+        tmem_ld32(tmem_o + lane_off + c0, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+        tmem_ld32(tmem_o + lane_off + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+        tmem_ld_wait();
+        if (c0 == 64) {                            // all of O is in registers: the next item may start accumulating
+          tc_fence_before();
+          mbar_arrive(o_free);
+        }
+        if (valid) {
+#pragma unroll
+          for (int e = 0; e < 64; e += 8) {
+            uint4 pk4 = make_uint4(pack_bf16x2(__uint_as_float(o[e]) * inv_l, __uint_as_float(o[e + 1]) * inv_l),
+                                   pack_bf16x2(__uint_as_float(o[e + 2]) * inv_l, __uint_as_float(o[e + 3]) * inv_l),
+                                   pack_bf16x2(__uint_as_float(o[e + 4]) * inv_l, __uint_as_float(o[e + 5]) * inv_l),
+                                   pack_bf16x2(__uint_as_float(o[e + 6]) * inv_l, __uint_as_float(o[e + 7]) * inv_l));
+            *reinterpret_cast<uint4*>(orow + c0 + e) = pk4;
+          }
         }
       }
     }
@@ -337,7 +383,11 @@ extern "C" int svr2_attn_varlen_bf16(const void* q, const void* k, const void* v
   p.out = (__nv_bfloat16*)out;
   p.heads = heads;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)ATT_D);
-  dim3 grid((max_seqlen + ATT_BM - 1) / ATT_BM, n_seq, heads);
+  p.n_qt = (max_seqlen + ATT_BM - 1) / ATT_BM;
+  const long long n_work = (long long)p.n_qt * n_seq * heads;
+  if (n_work > 0x7fffffffLL) return set_error(SVR2_ERR_ARG, "svr2_attn_varlen_bf16: too many work items");
+  p.n_work = (int)n_work;
+  const int grid = (int)(n_work < 2LL * num_sms() ? n_work : 2LL * num_sms());   // persistent: two CTAs per SM
   attn_varlen_kernel<<<grid, ATT_THREADS, AttnSmem::kTotal, (cudaStream_t)stream>>>(tq, tk, tv, p);
   return check_launch("attn_varlen");
 }

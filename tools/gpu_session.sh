@@ -13,6 +13,12 @@ for s in $STAGES; do
     ncu_attn) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_varlen -c 1 -f -o gpurun_out/r2_attn python tools/perf_conv_one.py attn > gpurun_out/r2_ncu_attn.log 2>&1; tail -3 gpurun_out/r2_ncu_attn.log ;;
     bench)    timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r2_bench_4k.json 2> gpurun_out/r2_bench_4k.err; cut -c1-1500 gpurun_out/r2_bench_4k.json ;;
     bench1080) timeout 600 python bench.py --workload 1080p --steps 5 --warmup 3 --phases --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_1080p.json 2> gpurun_out/r2_bench_1080p_phases.txt; cut -c1-600 gpurun_out/r2_bench_1080p.json ;;
+    glb_ops)  timeout 600 python tools/gpu_library_baseline.py --ops --out gpurun_out/r2_gpu_library_ops.json > gpurun_out/r2_glb_ops.log 2>&1; grep -A8 '"attn_243' gpurun_out/r2_glb_ops.log | head -12 ;;
+    bench7b)  timeout 600 python bench.py --workload 4k_shard_7b --steps 3 --warmup 2 --phases --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_4k_shard_7b.json 2> gpurun_out/r2_bench_4k_shard_7b_phases.txt; cut -c1-500 gpurun_out/r2_bench_4k_shard_7b.json ;;
+    clip64)   timeout 900 python bench.py --workload 4k_clip64 --steps 2 --warmup 1 --phases --lib-baseline none --no-cpu-baseline --no_graph > gpurun_out/r2_bench_4k_clip64.json 2> gpurun_out/r2_bench_4k_clip64_phases.txt; cut -c1-500 gpurun_out/r2_bench_4k_clip64.json ;;
+    sweep)    for T in 16 32 64 128; do timeout 600 python bench.py --workload vae_decode_T$T --steps 3 --warmup 2 --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_vae_decode_T$T.json 2> gpurun_out/r2_bench_vae_decode_T$T.err; cut -c1-330 gpurun_out/r2_bench_vae_decode_T$T.json; echo; done ;;
+    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2_launches.csv python bench.py --workload 1080p --steps 1 --warmup 1 --no_graph --lib-baseline none --no-cpu-baseline > gpurun_out/r2_launches_bench.log 2>&1; tail -2 gpurun_out/r2_launches_bench.log | cut -c1-300 ;;
+    ncu_conv) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -c 1 -f -o gpurun_out/r2_conv256 python tools/perf_conv_one.py conv256 > gpurun_out/r2_ncu_conv256.log 2>&1; tail -2 gpurun_out/r2_ncu_conv256.log ;;
     *) echo "unknown stage $s" ;;
   esac
 done
