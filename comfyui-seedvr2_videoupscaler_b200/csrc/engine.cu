@@ -126,6 +126,7 @@ struct svr2_engine {
   std::map<std::vector<int>, Geometry*> geo;      // (T, Hp, Wp, l) -> tables
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
+  std::vector<void*> retired_workspaces;          // outgrown blocks: a captured CUDA graph may still replay into them
   char err[256] = "";
 };
 
@@ -386,6 +387,7 @@ extern "C" void svr2_destroy(svr2_t* e) {
     delete kv.second;
   }
   if (e->workspace) cudaFree(e->workspace);
+  for (void* p : e->retired_workspaces) cudaFree(p);
   delete e;
 }
 
@@ -473,8 +475,9 @@ extern "C" int svr2_dit_forward(svr2_t* e, const void* vid, const void* txt, int
   const int max_win = g->lay[0].n_win > g->lay[1].n_win ? g->lay[0].n_win : g->lay[1].n_win;
   const Plan P = make_plan(D, T, H, W, l, max_total, L + max_win * l, fuse);
   if (P.total > e->workspace_bytes) {
-    cudaStreamSynchronize((cudaStream_t)stream);     // nothing queued may still use the old block
-    if (e->workspace) cudaFree(e->workspace);
+    // grow: the outgrown block is kept until svr2_destroy — work already queued, or a captured CUDA graph of a smaller
+    // geometry, may still use it (freeing it would hand its address to someone else)
+    if (e->workspace) e->retired_workspaces.push_back(e->workspace);
     e->workspace = nullptr;
     e->workspace_bytes = 0;
     if (cudaMalloc(&e->workspace, P.total) != cudaSuccess) return fail(e, SVR2_ERR_CUDA, "svr2_dit_forward: workspace allocation failed");
