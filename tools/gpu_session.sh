@@ -19,6 +19,8 @@ for s in $STAGES; do
     sweep)    for T in 16 32 64 128; do timeout 600 python bench.py --workload vae_decode_T$T --steps 3 --warmup 2 --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_vae_decode_T$T.json 2> gpurun_out/r2_bench_vae_decode_T$T.err; cut -c1-330 gpurun_out/r2_bench_vae_decode_T$T.json; echo; done ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2_launches.csv python bench.py --workload 1080p --steps 1 --warmup 1 --no_graph --lib-baseline none --no-cpu-baseline > gpurun_out/r2_launches_bench.log 2>&1; tail -2 gpurun_out/r2_launches_bench.log | cut -c1-300 ;;
     ncu_conv) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -c 1 -f -o gpurun_out/r2_conv256 python tools/perf_conv_one.py conv256 > gpurun_out/r2_ncu_conv256.log 2>&1; tail -2 gpurun_out/r2_ncu_conv256.log ;;
+    debug_native) timeout 300 python tools/debug_native.py > gpurun_out/r2_debug_native.log 2>&1; cat gpurun_out/r2_debug_native.log | tail -14 ;;
+    tests_attn) timeout 600 python -m pytest tests -m gpu -q -k "attn or attention or dit_vs_golden or native" > gpurun_out/r2_pytest_attn.log 2>&1; tail -8 gpurun_out/r2_pytest_attn.log ;;
     *) echo "unknown stage $s" ;;
   esac
 done
