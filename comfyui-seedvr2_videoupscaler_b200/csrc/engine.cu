@@ -147,6 +147,12 @@ template <typename T>
 T* upload(Geometry* g, const std::vector<T>& host) {
   void* d = nullptr;
   if (host.empty()) return nullptr;
+#ifdef SVR2_HOST_TEST      // geometry unit tests on a box without a GPU: tables stay in host memory
+  d = malloc(host.size() * sizeof(T));
+  memcpy(d, host.data(), host.size() * sizeof(T));
+  g->allocs.push_back(d);
+  return reinterpret_cast<T*>(d);
+#endif
   if (cudaMalloc(&d, host.size() * sizeof(T)) != cudaSuccess) return nullptr;
   cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
   g->allocs.push_back(d);
@@ -234,7 +240,9 @@ bool build_rope_table(Geometry* g, RopeTable& tab, const std::vector<float>& fre
       const int n = kv.first, off = kv.second;
       const float step = n > 1 ? 2.0f / (float)(n - 1) : 0.f;
       for (int i = 0; i < n && off + i < rows; ++i) {
-        const float v = i < n / 2 ? -1.0f + step * (float)i : 1.0f - step * (float)(n - 1 - i);
+        // torch's CPU linspace evaluates both halves with a fused multiply-add (the centre of an odd-length axis is
+        // -2^-24, not 0)
+        const float v = i < n / 2 ? fmaf(step, (float)i, -1.0f) : fmaf(-step, (float)(n - 1 - i), 1.0f);
         pos[off + i] = round_to(n > 1 ? v : -1.0f, fdtype);
       }
     }
