@@ -10,10 +10,9 @@
 //   warp 0    : TMA producer  (Q once, then a 2-stage ring of K/V tiles, 128B swizzle)
 //   warp 1    : MMA issuer    (S = Q K^T and O += P V, tcgen05.mma M=128,N=128,K=16, fp32 in TMEM;
 //                              V is consumed straight from its row-major tile as an MN-major B operand)
-//   warps 2-9 : softmax       (two threads per query row — warps w and w+4 share a TMEM lane quadrant and own one
-//                              half of the tile's 64 score columns each: tcgen05.ld the half row, exchange the
-//                              half-row maxima through smem, exp2 in registers, P -> bf16 -> swizzled smem as the
-//                              A operand of P·V, thresholded rescale of O in TMEM, final 1/l and store)
+//   warps 2-5 : softmax       (one query row per thread: tcgen05.ld the S row, online softmax in
+//                              registers with exp2, P -> bf16 -> swizzled smem as the A operand of P·V,
+//                              lazy rescale of O in TMEM, final 1/l and store)
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -34,7 +33,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 constexpr int ATT_BM = 128;      // q rows per CTA
 constexpr int ATT_BN = 64;       // kv rows per tile (two CTAs are co-resident per SM: ~98 KB smem each)
 constexpr int ATT_D = 128;
-constexpr int ATT_THREADS = 320;     // producer warp, MMA warp, 8 softmax warps (two per TMEM lane quadrant)
+constexpr int ATT_THREADS = 192;
 constexpr int ATT_Q_BYTES = 128 * 128 * 2;          // 32 KB: two [128 x 64] swizzled halves
 constexpr int ATT_QH_BYTES = ATT_Q_BYTES / 2;
 constexpr int ATT_KV_BYTES = ATT_BN * 128 * 2;      // 16 KB: two [64 x 64] swizzled halves
@@ -49,8 +48,7 @@ struct AttnSmem {
   static constexpr int kV = kK + ATT_KV_BYTES;
   static constexpr int kK1 = kV + ATT_KV_BYTES;      // second K stage
   static constexpr int kBar = kK1 + ATT_KV_BYTES;
-  static constexpr int kXchg = kBar + 128;            // [2 buffers][2 column halves][128 rows] fp32 row statistics
-  static constexpr int kTotal = kXchg + 2 * 2 * 128 * 4 + 1024;
+  static constexpr int kTotal = kBar + 128 + 1024;
 };
 
 struct AttnParams {
@@ -104,11 +102,11 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(s_free, 256);
-    mbar_init(p_ready, 256);
+    mbar_init(s_free, 128);
+    mbar_init(p_ready, 128);
     mbar_init(pv_done, 1);
     mbar_init(q_empty, 1);
-    mbar_init(o_free, 256);
+    mbar_init(o_free, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);     // S: 64 columns, O: 128 columns
@@ -224,26 +222,17 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       }
     }
   } else {
-    // ------------------------------ softmax warps (2..9)
-    // Two threads per query row: warps w and w + 4 address the same TMEM lane quadrant (w & 3) and own the low / high
-    // 32 score columns of every 64-column tile, so an SM runs 16 softmax warps (4 per scheduler) instead of 8 — the
-    // per-tile chain (TMEM load -> max -> exp2 -> pack -> store -> fence -> arrive) is latency-bound, not throughput-
-    // bound.  The two half-row maxima meet through smem (one named barrier per quadrant and tile); the row sums stay
-    // per thread and meet once, in the epilogue.
+    // ------------------------------ softmax warps (2..5)
     const int quad = warp & 3;                 // TMEM lane quadrant accessible to this warp
-    const int half = (warp - 2) >> 2;          // which 32 of the tile's 64 score columns / which 64 of O's 128
     const int row = quad * 32 + lane;          // query row within the tile
     const uint32_t lane_off = uint32_t(quad * 32) << 16;
-    constexpr int HC = ATT_BN / 2;             // score columns per thread
     // m_ref is the row maximum the exponentials are taken against.  It only moves when the running maximum has grown
     // by more than 2^kGrow since (FA4's thresholded rescale): P then holds values up to 2^kGrow instead of <= 1 — exact
-    // in fp32 / bf16 (relative rounding), and the O rescale below (TMEM round trips on the critical path) becomes
+    // in fp32 / bf16 (relative rounding), and the O rescale below (four TMEM round trips on the critical path) becomes
     // rare instead of happening on almost every early tile.
     constexpr float kGrow = 8.0f;
     const float sc = p.scale_log2;
     const uint32_t sp_row = smem_u32(smem + AttnSmem::kP) + row * 128;
-    float* xchg = reinterpret_cast<float*>(smem + AttnSmem::kXchg);
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
     uint32_t g = 0;                            // tiles processed by this CTA (phase of s_full / s_free / p_ready / pv_done)
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       int qt, head, s_begin, len;
@@ -254,32 +243,29 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       for (int j = 0; j < n_kv; ++j, ++g) {
         mbar_wait(s_full, g & 1);
         tc_fence_after();
-        uint32_t sv[HC];
-        tmem_ld32(tmem_s + lane_off + half * HC, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        uint32_t sv[ATT_BN];
+        tmem_ld32(tmem_s + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_ld32(tmem_s + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(s_free);                      // S may be overwritten by the next QK^T
-        const int kv_valid = len - j * ATT_BN - half * HC;    // columns >= kv_valid are padding / the next sequence
-        if (kv_valid < HC) {                      // only the last tile of a sequence is ragged
+        const int kv_valid = len - j * ATT_BN;    // columns >= kv_valid are padding / the next sequence
+        if (kv_valid < ATT_BN) {                  // only the last tile of a sequence is ragged
 #pragma unroll
-          for (int c = 0; c < HC; ++c)
+          for (int c = 0; c < ATT_BN; ++c)
             if (c >= kv_valid) sv[c] = 0xff800000u;   // -inf
         }
-        // half-row maximum: four independent chains of 3-input max, then the partner's half through smem
+        // row maximum: four independent chains of 3-input max
         float mx4[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) mx4[a] = __uint_as_float(sv[a]);
 #pragma unroll
-        for (int c = 4; c < HC; c += 8) {
+        for (int c = 4; c < ATT_BN; c += 8) {
 #pragma unroll
           for (int a = 0; a < 4; ++a)
-            mx4[a] = fmaxf(fmaxf(mx4[a], __uint_as_float(sv[c + a])), __uint_as_float(sv[(c + 4 + a) & (HC - 1)]));
+            mx4[a] = fmaxf(fmaxf(mx4[a], __uint_as_float(sv[c + a])), __uint_as_float(sv[(c + 4 + a) & (ATT_BN - 1)]));
         }
-        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        float* xb = xchg + (g & 1) * 256;
-        xb[half * 128 + row] = mx;
-        pair_sync();
-        mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         const bool grow = (mx - m_ref) * sc > kGrow;                   // true on the first tile (m_ref = -inf)
         const float m_new = grow ? mx : m_ref;
         const float alpha = grow ? fast_exp2((m_ref - m_new) * sc) : 1.0f;   // 0 on the first tile
@@ -287,9 +273,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const float2 sc2 = make_float2(sc, sc);
         // P = exp2(s * sc - m_new * sc): packed fp32x2 FMAs, four independent partial sums
         float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        uint32_t pk[HC / 2];
+        uint32_t pk[ATT_BN / 2];
 #pragma unroll
-        for (int c = 0; c < HC; c += 2) {
+        for (int c = 0; c < ATT_BN; c += 2) {
           const float2 t = ffma2(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sc2, nmb);
           const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
           ls[(c >> 1) & 1] = fadd2(ls[(c >> 1) & 1], e);
@@ -299,55 +285,53 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         if (j > 0) {
           mbar_wait(pv_done, (g - 1) & 1);        // P_{j-1} V_{j-1} has read the P buffer and updated O
           tc_fence_after();
-          if (__any_sync(0xffffffffu, grow)) {    // this thread's half of the O row
+          if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
-            for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
-              uint32_t o[32];
-              tmem_ld32(tmem_o + lane_off + c0, o);
+            for (int c0 = 0; c0 < 128; c0 += 64) {
+              uint32_t o[64];
+              tmem_ld32(tmem_o + lane_off + c0, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+              tmem_ld32(tmem_o + lane_off + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
               tmem_ld_wait();
 #pragma unroll
-              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-              tmem_st32(tmem_o + lane_off + c0, o);
+              for (int e = 0; e < 64; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st32(tmem_o + lane_off + c0, *reinterpret_cast<const uint32_t(*)[32]>(&o[0]));
+              tmem_st32(tmem_o + lane_off + c0 + 32, *reinterpret_cast<const uint32_t(*)[32]>(&o[32]));
             }
             tmem_st_wait();
           }
         }
-        // P -> swizzled K-major smem (row = this thread's query row, its 4 of the row's 8 chunks of 16 B)
+        // P -> swizzled K-major smem (row = this thread, 8 chunks of 16 B); explicit shared-space stores
 #pragma unroll
-        for (int ch = 0; ch < HC / 8; ++ch)
-          st_shared_v4(sp_row + (((half * (HC / 8) + ch) ^ (row & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2],
-                       pk[4 * ch + 3]);
+        for (int ch = 0; ch < ATT_BN / 8; ++ch)
+          st_shared_v4(sp_row + ((ch ^ (row & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
         l_run = l_run * alpha + lsum;
         m_ref = m_new;
         fence_proxy_async_smem();                  // make P visible to the tensor core (async proxy)
         tc_fence_before();
         mbar_arrive(p_ready);
       }
-      // ------------------------------ epilogue: O / l -> bf16 -> global (this thread: 64 of the row's 128 columns)
-      float* xb = xchg + (g & 1) * 256;            // the buffer the next tile would use: free (its last reader passed a pair_sync)
-      xb[half * 128 + row] = l_run;
-      pair_sync();
-      const float inv_l = 1.0f / (l_run + xb[(half ^ 1) * 128 + row]);
-      pair_sync();                                 // both halves have read before the next item's first tile writes here
+      // ------------------------------ epilogue: O / l -> bf16 -> global
       mbar_wait(pv_done, (g - 1) & 1);
       tc_fence_after();
+      const float inv_l = 1.0f / l_run;
       const int q_idx = qt * ATT_BM + row;
       const bool valid = q_idx < len;
       long long grow_ = (long long)(s_begin + q_idx);
       if (valid && p.out_row_map) grow_ = p.out_row_map[grow_];
-      __nv_bfloat16* orow = p.out + (grow_ * p.heads + head) * ATT_D + half * 64;
+      __nv_bfloat16* orow = p.out + (grow_ * p.heads + head) * ATT_D;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t o[32];
-        tmem_ld32(tmem_o + lane_off + half * 64 + c0, o);
+      for (int c0 = 0; c0 < 128; c0 += 64) {
+        uint32_t o[64];
+        tmem_ld32(tmem_o + lane_off + c0, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+        tmem_ld32(tmem_o + lane_off + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
         tmem_ld_wait();
-        if (c0 == 32) {                            // all of this thread's O is in registers: the next item may accumulate
+        if (c0 == 64) {                            // all of O is in registers: the next item may start accumulating
           tc_fence_before();
           mbar_arrive(o_free);
         }
         if (valid) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 8) {
+          for (int e = 0; e < 64; e += 8) {
             uint4 pk4 = make_uint4(pack_bf16x2(__uint_as_float(o[e]) * inv_l, __uint_as_float(o[e + 1]) * inv_l),
                                    pack_bf16x2(__uint_as_float(o[e + 2]) * inv_l, __uint_as_float(o[e + 3]) * inv_l),
                                    pack_bf16x2(__uint_as_float(o[e + 4]) * inv_l, __uint_as_float(o[e + 5]) * inv_l),
