@@ -360,7 +360,8 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_gbs = peaks.get("hbm_gbs", 6500.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
-    gemm_names = ("svr2_linear_bf16", "svr2_conv3d_bf16", "svr2_conv3d_stats_bf16", "svr2_upsample_shuffle_bf16")
+    gemm_names = ("svr2_linear_bf16", "svr2_linear_ex_bf16", "svr2_linear_qkv_rope_bf16", "svr2_conv3d_bf16",
+                  "svr2_conv3d_stats_bf16", "svr2_conv3d_shortcut_stats_bf16", "svr2_upsample_shuffle_bf16")
     is_gemm = lambda n: n.split("|")[0] in gemm_names
     g_flops = sum(d["flops"] for n, d in prof.items() if is_gemm(n))
     g_ms = sum(d["ms"] for n, d in prof.items() if is_gemm(n))

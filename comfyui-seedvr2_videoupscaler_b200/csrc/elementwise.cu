@@ -634,6 +634,49 @@ __global__ void rowstat_combine_kernel(const float2* __restrict__ part, int slot
   if (lane == 0) lse[row] = mx + log2f(s);
 }
 
+// Single-pass variant (no duplicated Q K^T): a cheap GEMM over a SUBSET of the keys gives a reference exponent m^ per
+// row (any value within ~100 powers of two of the true row maximum works: probabilities are written un-normalised as
+// bf16(exp2(s - m^)) with full relative precision, their fp32 sum normalises the output afterwards).
+// partial [rows][slots] (max, sum) over the sampled keys -> mhat[row] = max; optionally clears the fallback flag.
+__global__ void rowstat_max_kernel(const float2* __restrict__ part, int slots, long long ld, float* __restrict__ mhat,
+                                   int rows, int* __restrict__ flag_reset) {
+  if (flag_reset && blockIdx.x == 0 && threadIdx.x == 0) *flag_reset = 0;
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float2* pr = part + row * ld;
+  float mx = -INFINITY;
+  for (int i = lane; i < slots; i += 32) mx = fmaxf(mx, pr[i].x);
+  mx = warp_max(mx);
+  if (lane == 0) mhat[row] = mx;
+}
+// partial [rows][slots] (max score, sum of exp2(score - mhat)) over ALL keys -> rowscale[row] = 1 / sum, and the safety
+// check of the reference exponent: the true maximum may exceed it by at most kMaxAbove powers of two (no overflow of the
+// bf16 probabilities / fp32 sums / fp32 accumulators) and the sum must be a positive finite number.  A violated row
+// raises *flag: the caller's conditional fallback launches then recompute the chunk with the exact two-pass kernels.
+__global__ void pexp_stat_combine_kernel(const float2* __restrict__ part, int slots, long long ld,
+                                         const float* __restrict__ mhat, float* __restrict__ rowscale, int rows,
+                                         int* __restrict__ flag) {
+  constexpr float kMaxAbove = 96.f;
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float2* pr = part + row * ld;
+  float mx = -INFINITY, s = 0.f;
+  for (int i = lane; i < slots; i += 32) {
+    const float2 v = pr[i];
+    mx = fmaxf(mx, v.x);
+    s += v.y;
+  }
+  mx = warp_max(mx);
+  s = warp_sum(s);
+  if (lane == 0) {
+    const bool ok = (s > 0.f) && (s < 3.0e38f) && (mx - mhat[row] <= kMaxAbove);
+    rowscale[row] = ok ? 1.0f / s : 0.f;
+    if (!ok) atomicOr(flag, 1);
+  }
+}
+
 // ------------------------------------------------------------------ transpose bf16 [rows, cols] -> [cols, rows]
 __global__ void transpose_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out,
                                  long long ld_out, int rows, int cols) {
@@ -943,6 +986,23 @@ extern "C" int svr2_rowstat_combine(const void* partial, int slots, int64_t ld, 
   if (rows <= 0) return SVR2_OK;
   rowstat_combine_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const float2*)partial, slots, ld, lse, rows);
   return check_launch("rowstat_combine");
+}
+
+extern "C" int svr2_rowstat_max(const void* partial, int slots, int64_t ld, float* mhat, int rows, int* flag_reset,
+                                void* stream) {
+  if (rows <= 0) return SVR2_OK;
+  rowstat_max_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const float2*)partial, slots, ld, mhat, rows,
+                                                                        flag_reset);
+  return check_launch("rowstat_max");
+}
+
+extern "C" int svr2_pexp_stat_combine(const void* partial, int slots, int64_t ld, const float* mhat, float* rowscale,
+                                      int rows, int* flag, void* stream) {
+  if (rows <= 0) return SVR2_OK;
+  if (!flag) return set_error(SVR2_ERR_ARG, "svr2_pexp_stat_combine: flag must not be NULL");
+  pexp_stat_combine_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const float2*)partial, slots, ld, mhat,
+                                                                              rowscale, rows, flag);
+  return check_launch("pexp_stat_combine");
 }
 
 extern "C" int svr2_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols,

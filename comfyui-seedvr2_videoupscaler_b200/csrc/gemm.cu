@@ -69,6 +69,11 @@ struct GemmParams {
   void* out;
   float4* stat_partial;           // conv only: [frame][slot][N/8] (sum0, sq0, sum1, sq1) of the stored values, or null
   int stat_slots;                 // slots per frame (tiles per frame x warps covering distinct rows)
+  // ---- single-pass attention probabilities (VAE mid-block attention without the duplicated Q K^T pass)
+  const float* rowscale;          // EPI_ROWSCALE: acc * rowscale[m] before everything else (P~ V / l)
+  float2* stat2;                  // KIND_PEXP: also emit per (row, column slot) (max of acc*out_scale, sum of the exponentials)
+  int ld_stat;                    // float2 slots per row of stat2
+  const int* run_if;              // launch is a no-op unless *run_if != 0 (device-side conditional fallback), or null
   // ---- KIND_QKV*: fused q/k RMSNorm + RoPE + window scatter (out = q, out2 = k, out3 = v, each [rows, inner])
   void* out2;
   void* out3;
@@ -92,6 +97,7 @@ enum : int {
   EPI_SILU = 128,     // t = bf16(silu(t))
   EPI_ROWSTAT = 256,  // out: per (row, n-tile half) partial (max, sum exp2) of acc*out_scale  (attention pass 1)
   EPI_PEXP = 512,     // out: bf16(exp2(acc*out_scale - rowvec[m]))                         (attention pass 2)
+  EPI_ROWSCALE = 1024,  // acc *= rowscale[m] first (un-normalised probabilities x V, divided by the row sum)
 };
 
 template <int BLOCK_N, bool TWO = false>
@@ -215,6 +221,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a2, const GemmParams p) {
   static_assert(!(SWAP && TWO), "swap-AB and CTA pairs are mutually exclusive");
+  if (p.run_if != nullptr && *p.run_if == 0) return;     // conditional launch: every thread of every CTA sees the same flag
   using L = SmemLayout<BLOCK_N, TWO>;
   const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
   constexpr int kStages = L::kStages;
@@ -557,9 +564,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_STRIDE;
 
       float row_lse = 0.f;
+      float st_mx = -INFINITY, st_sum = 0.f;       // KIND_PEXP with stat2: this thread's (row, column slot) statistics
       if constexpr (KIND == KIND_PEXP) {
         const int m = m_blk * BLOCK_M + row;
         row_lse = (m < p.M) ? gate[m] : 0.f;
+      }
+      float row_scale = 1.f;
+      if constexpr (KIND == KIND_BF16) {
+        if (epi & EPI_ROWSCALE) {
+          const int m = m_blk * BLOCK_M + row;
+          row_scale = (p.a_mode == 0 && m < p.M) ? p.rowscale[m] : 1.f;
+        }
       }
       if constexpr (KIND == KIND_QKV21 || KIND == KIND_QKV10) {
         // NaSwinAttention between the QKV projection and the attention call (mmattn.py:199-248, rope.py:116-176), in
@@ -723,8 +738,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               float a = __uint_as_float(i < 16 ? v0[2 * (i & 15)] : v1[2 * (i & 15)]);
               float b = __uint_as_float(i < 16 ? v0[2 * (i & 15) + 1] : v1[2 * (i & 15) + 1]);
               if constexpr (KIND == KIND_PEXP) {
-                pk[i] = pack_bf16x2(exp2_approx(fmaf(a, sc, -row_lse)), exp2_approx(fmaf(b, sc, -row_lse)));
+                const float ea = exp2_approx(fmaf(a, sc, -row_lse)), eb = exp2_approx(fmaf(b, sc, -row_lse));
+                pk[i] = pack_bf16x2(ea, eb);
+                if (p.stat2) {                      // columns past N are zero-padded operands, not scores
+                  const int cn = n_base + ph0 + 2 * i;
+                  if (cn + 1 < p.N) {
+                    st_sum += ea + eb;
+                    st_mx = fmaxf(st_mx, fmaxf(a, b));
+                  } else if (cn < p.N) {
+                    st_sum += ea;
+                    st_mx = fmaxf(st_mx, a);
+                  }
+                }
               } else {
+                if (epi & EPI_ROWSCALE) {
+                  a *= row_scale;
+                  b *= row_scale;
+                }
                 if (epi & EPI_BIAS) {
                   const uint32_t bw_ = __shfl_sync(0xffffffffu, bias_pk[phi], i);
                   a += __uint_as_float(bw_ << 16);
@@ -922,6 +952,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           __syncwarp();
+        }
+        if constexpr (KIND == KIND_PEXP) {
+          if (p.stat2) {     // this thread's row over this warp's columns of the tile: (max score, sum of exponentials)
+            const int m = m_blk * BLOCK_M + row;
+            if (m < p.M && !(TWO && m_blk >= p.num_m_tiles)) {
+              const int slot = (N_COLS >= 64) ? n_blk * 2 + half : n_blk;
+              p.stat2[(long long)m * p.ld_stat + slot] = make_float2(st_mx * p.out_scale, st_sum);
+            }
+          }
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -1138,9 +1177,33 @@ using namespace svr2;
 // ----------------------------------------------------------------------------
 // C ABI
 // ----------------------------------------------------------------------------
+static int linear_impl(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K, int epi_flags,
+                       const void* bias, const float* gate, const void* residual, void* out, int64_t ldc, float out_scale,
+                       const float* rowscale, void* stat_out, int64_t ld_stat, const int* run_if, void* stream);
+
 extern "C" int svr2_linear_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K,
                                 int epi_flags, const void* bias, const float* gate, const void* residual, void* out,
                                 int64_t ldc, float out_scale, void* stream) {
+  return linear_impl(a, lda, w, ldw, M, N, K, epi_flags, bias, gate, residual, out, ldc, out_scale, nullptr, nullptr, 0,
+                     nullptr, stream);
+}
+
+// svr2_linear_bf16 with the extras of the single-pass attention probabilities:
+//   rowscale (with SVR2_EPI_ROWSCALE): acc * rowscale[m] before the rest of the epilogue;
+//   stat_out (with SVR2_EPI_PEXP, N >= 256): float2 [M][ld_stat] = per (row, 128-column slot) (max acc*out_scale, sum of the
+//     exponentials written), ld_stat >= 2 * ceil(N / 256);
+//   run_if: device flag — the launch does nothing unless *run_if != 0 (conditional fallback without a host sync).
+extern "C" int svr2_linear_ex_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K,
+                                   int epi_flags, const void* bias, const float* gate, const void* residual, void* out,
+                                   int64_t ldc, float out_scale, const float* rowscale, void* stat_out, int64_t ld_stat,
+                                   const int* run_if, void* stream) {
+  return linear_impl(a, lda, w, ldw, M, N, K, epi_flags, bias, gate, residual, out, ldc, out_scale, rowscale, stat_out,
+                     ld_stat, run_if, stream);
+}
+
+static int linear_impl(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K, int epi_flags,
+                       const void* bias, const float* gate, const void* residual, void* out, int64_t ldc, float out_scale,
+                       const float* rowscale, void* stat_out, int64_t ld_stat, const int* run_if, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(SVR2_ERR_ARG, "svr2_linear_bf16: empty problem");
   const bool f32 = (epi_flags & EPI_F32) != 0, rowstat = (epi_flags & EPI_ROWSTAT) != 0;
   if ((lda % 8) || (ldw % 8) || (!rowstat && ((ldc % (f32 ? 4 : 8)) || (N % (f32 ? 4 : 8)))))
@@ -1182,6 +1245,14 @@ extern "C" int svr2_linear_bf16(const void* a, int64_t lda, const void* w, int64
   if (rowstat && ldc < (int64_t)p.num_n_tiles * (bn >= 64 ? 2 : 1))
     return set_error(SVR2_ERR_ARG, "EPI_ROWSTAT: ldc (float2 slots per row) must be >= svr2_rowstat_slots(N)");
   if ((p.epi & EPI_RESIDUAL) && !residual) return set_error(SVR2_ERR_ARG, "EPI_RESIDUAL without residual");
+  if ((p.epi & EPI_ROWSCALE) && (!rowscale || bn < 128 || (p.epi & (EPI_SWIGLU | EPI_ROWSTAT | EPI_PEXP | EPI_F32))))
+    return set_error(SVR2_ERR_ARG, "EPI_ROWSCALE needs rowscale, a plain bf16 epilogue and N >= 128");
+  if (stat_out && (!(p.epi & EPI_PEXP) || bn != 256 || ld_stat < 2 * (int64_t)p.num_n_tiles))
+    return set_error(SVR2_ERR_ARG, "stat_out needs EPI_PEXP, N >= 256 and ld_stat >= 2 * ceil(N / 256)");
+  p.rowscale = rowscale;
+  p.stat2 = reinterpret_cast<float2*>(stat_out);
+  p.ld_stat = (int)ld_stat;
+  p.run_if = run_if;
   return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream, pair);
 }
 

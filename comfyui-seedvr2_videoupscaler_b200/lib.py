@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libsvr2.so")
 
 EPI_BIAS, EPI_GATE, EPI_RESIDUAL, EPI_SWIGLU, EPI_GELU, EPI_F32, EPI_SILU = 1, 2, 4, 8, 16, 32, 128
-EPI_ROWSTAT, EPI_PEXP = 256, 512
+EPI_ROWSTAT, EPI_PEXP, EPI_ROWSCALE = 256, 512, 1024
 
 class ModelDesc(ctypes.Structure):
     """svr2_model_desc (include/svr2.h)"""
@@ -64,6 +64,10 @@ SIGNATURES = {
     "svr2_groupnorm_bf16": [_P, _P, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, c_int, _P, c_int64, _P],
     "svr2_groupnorm_scratch_bytes": [c_int, c_int, c_int],
     "svr2_softmax_rows_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, _P],
+    "svr2_linear_ex_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, c_float, _P, _P,
+                            c_int64, _P, _P],
+    "svr2_rowstat_max": [_P, c_int, c_int64, _P, c_int, _P, _P],
+    "svr2_pexp_stat_combine": [_P, c_int, c_int64, _P, _P, c_int, _P, _P],
     "svr2_rowstat_slots": [c_int],
     "svr2_rowstat_combine": [_P, c_int, c_int64, _P, c_int, _P],
     "svr2_transpose_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, _P],
@@ -191,7 +195,7 @@ def _bf16c(t, name):
 
 
 def linear(a, w, *, bias=None, gate=None, residual=None, epi=0, out=None, out_scale=1.0, n_valid=None,
-           count_flops=True):
+           count_flops=True, rowscale=None, stat_out=None, run_if=None):
     """out = epi(a @ w^T).  a [M,K] (row stride lda), w [N,K]."""
     _bf16c(a, "a"), _bf16c(w, "w")
     M, K = a.shape
@@ -211,8 +215,15 @@ def linear(a, w, *, bias=None, gate=None, residual=None, epi=0, out=None, out_sc
     if residual is not None:
         assert residual.stride(0) == out.stride(0)
     ldc = out.stride(0) // 2 if epi & EPI_ROWSTAT else out.stride(0)   # ROWSTAT: float2 slots per row
-    call("svr2_linear_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epi, ptr(bias), ptr(gate),
-         ptr(residual), ptr(out), ldc, float(out_scale), stream(),
+    extras = ()
+    name = "svr2_linear_bf16"
+    if rowscale is not None or stat_out is not None or run_if is not None:
+        name = "svr2_linear_ex_bf16"
+        if rowscale is not None:
+            epi |= EPI_ROWSCALE
+        extras = (ptr(rowscale), ptr(stat_out), stat_out.stride(0) // 2 if stat_out is not None else 0, ptr(run_if))
+    call(name, ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, epi, ptr(bias), ptr(gate),
+         ptr(residual), ptr(out), ldc, float(out_scale), *extras, stream(),
          flops=2.0 * M * (n_valid if n_valid is not None else N) * K if count_flops else 0.0,
          tag=f"|{M}x{N}x{K}|e{epi}" if (PROFILER is not None and PROFILER.detail) else "")
     return out

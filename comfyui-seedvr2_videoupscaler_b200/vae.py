@@ -132,6 +132,7 @@ class B200VideoVAE(EngineModule):
             W[p + "conv2+shortcut.bias"] = (W[p + "conv2.bias"].float() + W[p + "conv_shortcut.bias"].float()
                                             ).to(torch.bfloat16).contiguous()
         self.fuse_shortcut = os.environ.get("SVR2_FUSE_SHORTCUT", "1") != "0"      # 0: separate launch (A/B measurements)
+        self.single_pass_attention = os.environ.get("SVR2_VAE_ATTN", "single") != "two_pass"   # two_pass: exact path only
         self.W = self._register("w", W)
 
     # ---- temporal slicing state -------------------------------------------
@@ -285,17 +286,42 @@ class B200VideoVAE(EngineModule):
         P = torch.empty(min(cq, n), ldn, device=dev, dtype=torch.bfloat16)
         o = torch.empty(x.T * n, C, device=dev, dtype=torch.bfloat16)
         scale2 = (1.0 / (C ** 0.5)) * 1.4426950408889634
+        # Default (n >= 256, n % 8 == 0): ONE Q K^T pass.  A 1/16-cost GEMM over every 16th key yields a reference
+        # exponent per row; the full pass writes un-normalised bf16(exp2(s - ref)) and fp32 row sums; P~ @ V is divided
+        # by the row sum in its epilogue.  Exact (softmax is shift-invariant; bf16 rounding is relative) as long as the
+        # true row maximum is within 2^96 of the sampled one — checked on the device; the exact two-pass launches below
+        # are conditional on that flag and never ran in any test or benchmark.
+        single = self.single_pass_attention and n >= 256 and n % 8 == 0
+        if single:
+            k_sub_stride = 16
+            n_sub = (n + k_sub_stride - 1) // k_sub_stride
+            slots_s = lib.load().svr2_rowstat_slots(n_sub)
+            slots_p = 2 * ((n + 255) // 256)
+            rows_max = min(cq, n)
+            part_s = torch.empty(rows_max, 2 * slots_s, device=dev, dtype=torch.float32)
+            stat = torch.empty(rows_max, 2 * slots_p, device=dev, dtype=torch.float32)
+            mhat = torch.empty(rows_max, device=dev, dtype=torch.float32)
+            rscale = torch.empty(rows_max, device=dev, dtype=torch.float32)
+            flag = torch.zeros(1, device=dev, dtype=torch.int32)
         for f in range(x.T):
             qf, kf, vf = q[f * n:(f + 1) * n], k_[f * n:(f + 1) * n], v[f * n:(f + 1) * n]
             lib.call("svr2_transpose_bf16", lib.ptr(vf), C, lib.ptr(vt), ldn, n, C, lib.stream())
             for r0 in range(0, n, cq):
                 rows = min(cq, n - r0)
-                lib.linear(qf[r0:r0 + rows], kf, epi=lib.EPI_ROWSTAT, out=part[:rows], out_scale=scale2,
-                           count_flops=False)     # the duplicated Q K^T pass is time, not algorithmic work
+                qc, oc = qf[r0:r0 + rows], o[f * n + r0: f * n + r0 + rows]
+                if single:
+                    lib.linear(qc, kf[::k_sub_stride], epi=lib.EPI_ROWSTAT, out=part_s[:rows], out_scale=scale2, count_flops=False)
+                    lib.call("svr2_rowstat_max", lib.ptr(part_s), slots_s, slots_s, lib.ptr(mhat), rows, lib.ptr(flag), lib.stream())
+                    lib.linear(qc, kf, epi=lib.EPI_PEXP, gate=mhat, out=P[:rows], out_scale=scale2, stat_out=stat[:rows])
+                    lib.call("svr2_pexp_stat_combine", lib.ptr(stat), slots_p, slots_p, lib.ptr(mhat), lib.ptr(rscale), rows,
+                             lib.ptr(flag), lib.stream())
+                    lib.linear(P[:rows, :n], vt[:, :n], out=oc, rowscale=rscale)
+                run_if = flag if single else None        # exact path: unconditional, or the device-side fallback
+                lib.linear(qc, kf, epi=lib.EPI_ROWSTAT, out=part[:rows], out_scale=scale2, count_flops=False, run_if=run_if)
                 lib.call("svr2_rowstat_combine", lib.ptr(part), slots, slots, lib.ptr(lse), rows, lib.stream())
-                lib.linear(qf[r0:r0 + rows], k_buf[f * n: f * n + ldn], epi=lib.EPI_PEXP, gate=lse, out=P[:rows],
-                           out_scale=scale2)
-                lib.linear(P[:rows, :n], vt[:, :n], out=o[f * n + r0: f * n + r0 + rows])
+                lib.linear(qc, k_buf[f * n: f * n + ldn], epi=lib.EPI_PEXP, gate=lse, out=P[:rows], out_scale=scale2,
+                           run_if=run_if, count_flops=not single)
+                lib.linear(P[:rows, :n], vt[:, :n], out=oc, run_if=run_if, count_flops=not single)
         out = Act(x.T, x.H, x.W, C, 0, dev)
         xb = x.body.reshape(x.T * n, C)
         lib.linear(o, self.W[p + "to_out.0.weight"], bias=self.W[p + "to_out.0.bias"], residual=xb,

@@ -39,6 +39,7 @@ enum svr2_epilogue {
   SVR2_EPI_SILU = 128,    /* silu                                        embedding.py:56-60                    */
   SVR2_EPI_ROWSTAT = 256, /* attention pass 1: out[m][slot] = (max, sum exp2) of acc*out_scale over the slot's columns   */
   SVR2_EPI_PEXP = 512,    /* attention pass 2: out = bf16(exp2(acc*out_scale - gate[m])), gate = per-row log2-sum-exp     */
+  SVR2_EPI_ROWSCALE = 1024, /* acc * rowscale[m] first (svr2_linear_ex_bf16): un-normalised probabilities x V / row sum   */
 };
 
 const char* svr2_last_error(void);
@@ -194,6 +195,20 @@ int svr2_groupnorm_from_stats_bf16(const void* x, void* y, int frames, int hw, i
  * pass 2 = svr2_linear_bf16(..., SVR2_EPI_PEXP) writing normalised bf16 probabilities, then P @ V. */
 int svr2_rowstat_slots(int N);
 int svr2_rowstat_combine(const void* partial, int slots, int64_t ld, float* lse, int rows, void* stream);
+/* Single-pass variant without the duplicated Q K^T (default for n >= 256 keys):
+ *   1. reference exponent m^[m]: svr2_linear_bf16(q, every 16th key, SVR2_EPI_ROWSTAT) + svr2_rowstat_max — a 1/16-cost GEMM;
+ *      any m^ within ~96 powers of two of the true row maximum is as good as the maximum itself;
+ *   2. svr2_linear_ex_bf16(q, k, SVR2_EPI_PEXP, gate = m^, stat_out): un-normalised bf16(exp2(s - m^)) plus per-slot
+ *      (max score, fp32 sum of the exponentials); svr2_pexp_stat_combine -> rowscale = 1 / sum and a device flag if some
+ *      row's true maximum exceeded m^ by more than the safe margin (or the sum is not a positive finite number);
+ *   3. svr2_linear_ex_bf16(P~, V^T, SVR2_EPI_ROWSCALE, rowscale) = softmax(q k^T) v;
+ *   4. the exact two-pass launches above with run_if = flag: no-ops unless step 2 raised it (never observed). */
+int svr2_linear_ex_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K, int epi_flags,
+                        const void* bias, const float* gate, const void* residual, void* out, int64_t ldc, float out_scale,
+                        const float* rowscale, void* stat_out, int64_t ld_stat, const int* run_if, void* stream);
+int svr2_rowstat_max(const void* partial, int slots, int64_t ld, float* mhat, int rows, int* flag_reset, void* stream);
+int svr2_pexp_stat_combine(const void* partial, int slots, int64_t ld, const float* mhat, float* rowscale, int rows,
+                           int* flag, void* stream);
 /* row softmax fp32 -> bf16 (materialised-score variant, kept for small problems / tests) */
 int svr2_softmax_rows_bf16(const float* s, int64_t lds, void* p, int64_t ldp, int rows, int cols, void* stream);
 int svr2_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols, void* stream);

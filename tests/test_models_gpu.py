@@ -300,3 +300,40 @@ def test_dit_native_runtime_equals_python_sequencing(pkg, name):
     eng.native = False
     assert torch.equal(o2, eng(vid2.cuda(), txt.cuda(), [[1, 16, 24]], [[l]]).vid_sample)
     assert torch.equal(out_n, dit.B200NaDiT(cfg, sd)(vid.cuda(), txt.cuda(), [[T, H, W]], [[l]]).vid_sample)
+
+
+def test_vae_attention_single_pass_equals_two_pass_and_falls_back(vae_pair):
+    """Mid-block attention (attn_video_vae.py:656-668): the single-pass path (sampled reference exponent, un-normalised
+    probabilities, row-sum division in the P V epilogue) against the exact two-pass path on the same input, and the
+    device-side fallback: keys crafted so that the true row maximum sits > 2^96 above every sampled key's score must
+    still give the exact result (the conditional two-pass launches run)."""
+    vae = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.vae")
+    eng, sd32 = vae_pair
+    p = "decoder.mid_block.attentions.0."
+    C, Hh, Ww = 512, 34, 60
+    n = Hh * Ww
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = vae.Act(2, Hh, Ww, C, 0, "cuda")
+    x.buf.copy_(torch.randn(x.buf.shape, generator=g, device="cuda", dtype=torch.bfloat16))
+
+    def run(single):
+        eng.single_pass_attention = single
+        try:
+            return eng._attention(x, p).buf.clone()
+        finally:
+            eng.single_pass_attention = True
+    a, b = run(True), run(False)
+    d = (a.float() - b.float()).abs()
+    assert psnr(a, b) > 60.0 and d.max() <= 2 ** -5 * b.abs().max().item(), f"single vs two-pass: {psnr(a, b):.1f} dB, max {d.max():.4f}"
+    # fallback: scale the K projection so that scores are huge and dominated by individual (mostly un-sampled) keys
+    wk, bk = eng.W[p + "to_k.weight"], eng.W[p + "to_k.bias"]
+    wk_saved, bk_saved = wk.clone(), bk.clone()
+    try:
+        wk.mul_(400.0)
+        bk.mul_(400.0)
+        a, b = run(True), run(False)
+        assert torch.isfinite(a).all() and torch.isfinite(b).all()
+        assert torch.equal(a, b), f"fallback must reproduce the exact path bit for bit ({psnr(a, b):.1f} dB)"
+    finally:
+        wk.copy_(wk_saved)
+        bk.copy_(bk_saved)
