@@ -221,7 +221,9 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a2, const GemmParams p) {
   static_assert(!(SWAP && TWO), "swap-AB and CTA pairs are mutually exclusive");
+#ifndef SVR2_AB_NO_RUNIF
   if (p.run_if != nullptr && *p.run_if == 0) return;     // conditional launch: every thread of every CTA sees the same flag
+#endif
   using L = SmemLayout<BLOCK_N, TWO>;
   const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
   constexpr int kStages = L::kStages;
@@ -565,6 +567,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
       float row_lse = 0.f;
       float st_mx = -INFINITY, st_sum = 0.f;       // KIND_PEXP with stat2: this thread's (row, column slot) statistics
+      float st_mx1 = -INFINITY, st_sum1 = 0.f;     // (second chain)
       if constexpr (KIND == KIND_PEXP) {
         const int m = m_blk * BLOCK_M + row;
         row_lse = (m < p.M) ? gate[m] : 0.f;
@@ -732,6 +735,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int phi = (ph0 - col_lo) / 64;
             uint32_t pk[32];
             const float sc = p.out_scale;
+            const bool want_stats = (KIND == KIND_PEXP) && p.stat2 != nullptr;
+            const bool stats_full = n_base + ph0 + 64 <= p.N;
             const bool plain = !(epi & (EPI_GELU | EPI_SILU | EPI_GATE));
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -740,21 +745,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               if constexpr (KIND == KIND_PEXP) {
                 const float ea = exp2_approx(fmaf(a, sc, -row_lse)), eb = exp2_approx(fmaf(b, sc, -row_lse));
                 pk[i] = pack_bf16x2(ea, eb);
-                if (p.stat2) {                      // columns past N are zero-padded operands, not scores
-                  const int cn = n_base + ph0 + 2 * i;
-                  if (cn + 1 < p.N) {
-                    st_sum += ea + eb;
-                    st_mx = fmaxf(st_mx, fmaxf(a, b));
-                  } else if (cn < p.N) {
-                    st_sum += ea;
-                    st_mx = fmaxf(st_mx, a);
+                if (want_stats) {
+                  if (stats_full) {                 // interior phase: two independent chains, no column tests
+                    if (i & 1) { st_sum1 += ea + eb; st_mx1 = fmaxf(fmaxf(st_mx1, a), b); }
+                    else { st_sum += ea + eb; st_mx = fmaxf(fmaxf(st_mx, a), b); }
+                  } else {                          // last n-tile: columns past N are zero-padded operands, not scores
+                    const int cn = n_base + ph0 + 2 * i;
+                    if (cn < p.N) { st_sum += ea; st_mx = fmaxf(st_mx, a); }
+                    if (cn + 1 < p.N) { st_sum += eb; st_mx = fmaxf(st_mx, b); }
                   }
                 }
               } else {
+#ifndef SVR2_AB_NO_ROWSCALE
                 if (epi & EPI_ROWSCALE) {
                   a *= row_scale;
                   b *= row_scale;
                 }
+#endif
                 if (epi & EPI_BIAS) {
                   const uint32_t bw_ = __shfl_sync(0xffffffffu, bias_pk[phi], i);
                   a += __uint_as_float(bw_ << 16);
@@ -958,7 +965,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int m = m_blk * BLOCK_M + row;
             if (m < p.M && !(TWO && m_blk >= p.num_m_tiles)) {
               const int slot = (N_COLS >= 64) ? n_blk * 2 + half : n_blk;
-              p.stat2[(long long)m * p.ld_stat + slot] = make_float2(st_mx * p.out_scale, st_sum);
+              p.stat2[(long long)m * p.ld_stat + slot] = make_float2(fmaxf(st_mx, st_mx1) * p.out_scale, st_sum + st_sum1);
             }
           }
         }
@@ -1215,7 +1222,8 @@ static int linear_impl(const void* a, int64_t lda, const void* w, int64_t ldw, i
   // CTAs would walk the whole K loop.  Narrower tiles spread the same work over up to half the SMs.
   if (!(epi_flags & (EPI_SWIGLU | EPI_ROWSTAT | EPI_PEXP))) {
     const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-    while (bn > 32 && 2 * m_tiles * ((N + bn - 1) / bn) <= num_sms()) bn /= 2;
+    const int bn_min = (epi_flags & EPI_ROWSCALE) ? 128 : 32;       // the row-scale epilogue lives in the wide path
+    while (bn > bn_min && 2 * m_tiles * ((N + bn - 1) / bn) <= num_sms()) bn /= 2;
   }
   CUtensorMap ta, tb;
   uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)lda * 2};

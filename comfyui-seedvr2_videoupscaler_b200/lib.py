@@ -12,7 +12,7 @@ from ctypes import c_float, c_int, c_int64, c_void_p, POINTER
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libsvr2.so")
+LIB_PATH = os.environ.get("SVR2_LIB") or os.path.join(HERE, "csrc", "libsvr2.so")   # SVR2_LIB: another build (A/B tools only)
 
 EPI_BIAS, EPI_GATE, EPI_RESIDUAL, EPI_SWIGLU, EPI_GELU, EPI_F32, EPI_SILU = 1, 2, 4, 8, 16, 32, 128
 EPI_ROWSTAT, EPI_PEXP, EPI_ROWSCALE = 256, 512, 1024

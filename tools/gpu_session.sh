@@ -21,6 +21,7 @@ for s in $STAGES; do
     ncu_conv) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -c 1 -f -o gpurun_out/r2_conv256 python tools/perf_conv_one.py conv256 > gpurun_out/r2_ncu_conv256.log 2>&1; tail -2 gpurun_out/r2_ncu_conv256.log ;;
     debug_native) timeout 300 python tools/debug_native.py > gpurun_out/r2_debug_native.log 2>&1; cat gpurun_out/r2_debug_native.log | tail -14 ;;
     tests_attn) timeout 600 python -m pytest tests -m gpu -q -k "attn or attention or dit_vs_golden or native" > gpurun_out/r2_pytest_attn.log 2>&1; tail -8 gpurun_out/r2_pytest_attn.log ;;
+    ab_upsample) for v in "" NO_RUNIF NO_ROWSCALE NO_BOTH; do for i in 1 2 3; do if [ -z "$v" ]; then L=""; else L="$PWD/comfyui-seedvr2_videoupscaler_b200/csrc/libsvr2_ab_$v.so"; fi; echo -n "lib=${v:-default} "; SVR2_LIB=$L python tools/perf_conv_one.py upsample 2>&1 | tail -1; done; done | tee gpurun_out/r2_ab_upsample.log ;;
     *) echo "unknown stage $s" ;;
   esac
 done
