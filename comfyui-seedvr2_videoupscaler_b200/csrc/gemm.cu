@@ -161,7 +161,10 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
 }
 
 enum : int { KIND_BF16 = 0, KIND_SWIGLU = 1, KIND_F32 = 2, KIND_ROWSTAT = 3, KIND_PEXP = 4,
-             KIND_QKV21 = 5, KIND_QKV10 = 6 };   // QKV projection + q/k RMSNorm + RoPE (21 / 10 frequencies per axis) + window scatter
+             KIND_QKV21 = 5, KIND_QKV10 = 6,
+             KIND_BF16_RS = 7,
+             KIND_PEXP_STAT = 8 };   // KIND_PEXP that also emits per-slot (max score, sum of exponentials)   // KIND_BF16 with a per-row scale on the accumulator (its own instantiation: a runtime test in
+                                   // the shared per-element loop cost the pixel-shuffle store 50 %)   // QKV projection + q/k RMSNorm + RoPE (21 / 10 frequencies per axis) + window scatter
 
 // One tile's output row of a thread: destination offset (elements), validity, halo duplication.
 struct RowDest {
@@ -221,9 +224,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a2, const GemmParams p) {
   static_assert(!(SWAP && TWO), "swap-AB and CTA pairs are mutually exclusive");
-#ifndef SVR2_AB_NO_RUNIF
   if (p.run_if != nullptr && *p.run_if == 0) return;     // conditional launch: every thread of every CTA sees the same flag
-#endif
   using L = SmemLayout<BLOCK_N, TWO>;
   const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
   constexpr int kStages = L::kStages;
@@ -431,6 +432,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // Phase 2: the warp re-reads the slab row-major so that every global load/store instruction covers
     //          contiguous 128-byte row segments (16 B per lane); residual loads are issued in batches
     //          before use, then add + store (+ halo copies).
+    constexpr bool IS_BF16 = KIND == KIND_BF16 || KIND == KIND_BF16_RS;
+    constexpr bool IS_PEXP = KIND == KIND_PEXP || KIND == KIND_PEXP_STAT;
     constexpr int N_COLS = KIND == KIND_SWIGLU ? ACC_STRIDE / 2 : ACC_STRIDE;   // output columns per tile
     constexpr int COLS_W = N_COLS >= 64 ? N_COLS / 2 : N_COLS;                 // columns per epilogue warp
     constexpr int PH_COLS = KIND == KIND_F32 ? 32 : (COLS_W < 64 ? COLS_W : 64);
@@ -547,11 +550,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // Wide path (64-column phases): per-column operands live in lane registers (lane l holds columns 2l, 2l+1
       // of the phase) and are broadcast by shuffle in phase 1; they are fetched before the accumulator wait so
       // the global-load latency never sits on the epilogue's critical path.
-      constexpr bool kWide = (KIND == KIND_BF16 || KIND == KIND_PEXP) && PH_COLS == 64;
+      constexpr bool kWide = (IS_BF16 || IS_PEXP) && PH_COLS == 64;
       constexpr int N_PH = kWide ? COLS_W / 64 : 1;
       uint32_t bias_pk[N_PH];
       float2 gate2[N_PH];
-      if constexpr (kWide && KIND == KIND_BF16) {
+      if constexpr (kWide && IS_BF16) {
 #pragma unroll
         for (int ph = 0; ph < N_PH; ++ph) {
           const int cn = n_base + col_lo + ph * 64 + 2 * lane;
@@ -568,16 +571,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       float row_lse = 0.f;
       float st_mx = -INFINITY, st_sum = 0.f;       // KIND_PEXP with stat2: this thread's (row, column slot) statistics
       float st_mx1 = -INFINITY, st_sum1 = 0.f;     // (second chain)
-      if constexpr (KIND == KIND_PEXP) {
+      if constexpr (IS_PEXP) {
         const int m = m_blk * BLOCK_M + row;
         row_lse = (m < p.M) ? gate[m] : 0.f;
       }
       float row_scale = 1.f;
-      if constexpr (KIND == KIND_BF16) {
-        if (epi & EPI_ROWSCALE) {
-          const int m = m_blk * BLOCK_M + row;
-          row_scale = (p.a_mode == 0 && m < p.M) ? p.rowscale[m] : 1.f;
-        }
+      if constexpr (KIND == KIND_BF16_RS) {
+        const int m = m_blk * BLOCK_M + row;
+        row_scale = (p.a_mode == 0 && m < p.M) ? p.rowscale[m] : 1.f;
       }
       if constexpr (KIND == KIND_QKV21 || KIND == KIND_QKV10) {
         // NaSwinAttention between the QKV projection and the attention call (mmattn.py:199-248, rope.py:116-176), in
@@ -735,17 +736,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int phi = (ph0 - col_lo) / 64;
             uint32_t pk[32];
             const float sc = p.out_scale;
-            const bool want_stats = (KIND == KIND_PEXP) && p.stat2 != nullptr;
+            constexpr bool want_stats = KIND == KIND_PEXP_STAT;
             const bool stats_full = n_base + ph0 + 64 <= p.N;
             const bool plain = !(epi & (EPI_GELU | EPI_SILU | EPI_GATE));
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               float a = __uint_as_float(i < 16 ? v0[2 * (i & 15)] : v1[2 * (i & 15)]);
               float b = __uint_as_float(i < 16 ? v0[2 * (i & 15) + 1] : v1[2 * (i & 15) + 1]);
-              if constexpr (KIND == KIND_PEXP) {
+              if constexpr (IS_PEXP) {
                 const float ea = exp2_approx(fmaf(a, sc, -row_lse)), eb = exp2_approx(fmaf(b, sc, -row_lse));
                 pk[i] = pack_bf16x2(ea, eb);
-                if (want_stats) {
+                if constexpr (want_stats) {
                   if (stats_full) {                 // interior phase: two independent chains, no column tests
                     if (i & 1) { st_sum1 += ea + eb; st_mx1 = fmaxf(fmaxf(st_mx1, a), b); }
                     else { st_sum += ea + eb; st_mx = fmaxf(fmaxf(st_mx, a), b); }
@@ -756,12 +757,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   }
                 }
               } else {
-#ifndef SVR2_AB_NO_ROWSCALE
-                if (epi & EPI_ROWSCALE) {
+                if constexpr (KIND == KIND_BF16_RS) {
                   a *= row_scale;
                   b *= row_scale;
                 }
-#endif
                 if (epi & EPI_BIAS) {
                   const uint32_t bw_ = __shfl_sync(0xffffffffu, bias_pk[phi], i);
                   a += __uint_as_float(bw_ << 16);
@@ -814,7 +813,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               const float sc = p.out_scale;
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * sc);
-            } else if constexpr (KIND == KIND_PEXP) {
+            } else if constexpr (IS_PEXP) {
               tmem_ld_wait();
               const float sc = p.out_scale;
 #pragma unroll
@@ -908,7 +907,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               off[i] = __shfl_sync(0xffffffffu, dst.off, r);
               const int f = __shfl_sync(0xffffffffu, dst.valid | (dst.dup << 1), r);
               flags[i] = col_ok ? f : 0;
-              if constexpr (KIND == KIND_BF16) {
+              if constexpr (IS_BF16) {
                 if ((epi & EPI_RESIDUAL) && (flags[i] & 1)) rv[i] = *reinterpret_cast<const uint4*>(resid + off[i] + col);
               }
             }
@@ -921,7 +920,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + off[i] + col) = d;
               } else {
                 __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
-                if constexpr (KIND == KIND_BF16) {
+                if constexpr (IS_BF16) {
                   if (epi & EPI_RESIDUAL) {
                     const uint32_t dw[4] = {d.x, d.y, d.z, d.w}, rw[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
                     uint32_t o[4];
@@ -933,7 +932,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   }
                 }
                 *reinterpret_cast<uint4*>(ob + off[i] + col) = d;
-                if constexpr (KIND == KIND_BF16) {
+                if constexpr (IS_BF16) {
                   if (p.stat_partial) stat_acc(st, d);
                 }
                 if (flags[i] & 2) {
@@ -943,7 +942,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
             }
           }
-          if constexpr (KIND == KIND_BF16) {
+          if constexpr (IS_BF16) {
             if (p.stat_partial && p.a_mode != 0) {
               // lanes with equal (lane % CPR) own the same channel octet for different rows
 #pragma unroll
@@ -960,7 +959,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           __syncwarp();
         }
-        if constexpr (KIND == KIND_PEXP) {
+        if constexpr (KIND == KIND_PEXP_STAT) {
           if (p.stat2) {     // this thread's row over this warp's columns of the tile: (max score, sum of exponentials)
             const int m = m_blk * BLOCK_M + row;
             if (m < p.M && !(TWO && m_blk >= p.num_m_tiles)) {
@@ -1124,6 +1123,16 @@ static int dispatch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& 
       case 128: return launch_gemm<128, KIND_BF16>(ta, tb, p, s, ta2);
     }
     return set_error(SVR2_ERR_ARG, "fused shortcut: Cout must be >= 128");
+  }
+  if (p.epi & EPI_ROWSCALE) {
+    if (pair) return launch_gemm<256, KIND_BF16_RS, false, true>(ta, tb, p, s);
+    if (block_n == 256) return launch_gemm<256, KIND_BF16_RS>(ta, tb, p, s);
+    if (block_n == 128) return launch_gemm<128, KIND_BF16_RS>(ta, tb, p, s);
+    return set_error(SVR2_ERR_ARG, "EPI_ROWSCALE needs >= 128-column tiles");
+  }
+  if ((p.epi & EPI_PEXP) && p.stat2) {
+    if (block_n != 256) return set_error(SVR2_ERR_ARG, "EPI_PEXP statistics need 256-column tiles");
+    return pair ? launch_gemm<256, KIND_PEXP_STAT, false, true>(ta, tb, p, s) : launch_gemm<256, KIND_PEXP_STAT>(ta, tb, p, s);
   }
   if (pair) {
     if (p.epi & EPI_SWIGLU) return launch_gemm<256, KIND_SWIGLU, false, true>(ta, tb, p, s);
