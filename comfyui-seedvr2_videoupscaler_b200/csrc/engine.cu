@@ -465,8 +465,25 @@ extern "C" size_t svr2_workspace_bytes(svr2_t* e, int T, int H, int W, int txt_l
 // One NaDiT forward: vid [T*H*W, in_ch] bf16 (latent pixels, channels last), txt [txt_len, txt_in_dim] bf16 ->
 // out [T*H*W, out_ch] bf16 (= NaDiTOutput.vid_sample).  Stream-ordered; the first call for a geometry builds and
 // uploads its index tables (synchronous copies) and may grow the workspace (cudaMalloc) — warm up before a graph capture.
+static int dit_forward_impl(svr2_t* e, const void* vid, const void* txt, int T, int H, int W, int txt_len, void* out,
+                            void* ext_ws, size_t ext_ws_bytes, void* stream);
+
 extern "C" int svr2_dit_forward(svr2_t* e, const void* vid, const void* txt, int T, int H, int W, int txt_len, void* out,
                                 void* stream) {
+  return dit_forward_impl(e, vid, txt, T, H, W, txt_len, out, nullptr, 0, stream);
+}
+
+// Same forward in a CALLER-provided workspace of at least svr2_workspace_bytes(...) bytes (256-byte aligned): nothing is
+// allocated or retained by the engine, so a host that pools device memory (PyTorch's caching allocator, a CUDA-graph
+// capture pool) gets the bytes back for the next phase — at 550 800 tokens (65-frame 4K clip) that is 35 GB.
+extern "C" int svr2_dit_forward_ws(svr2_t* e, const void* vid, const void* txt, int T, int H, int W, int txt_len,
+                                   void* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace) return set_error(SVR2_ERR_ARG, "svr2_dit_forward_ws: workspace must not be NULL");
+  return dit_forward_impl(e, vid, txt, T, H, W, txt_len, out, workspace, workspace_bytes, stream);
+}
+
+static int dit_forward_impl(svr2_t* e, const void* vid, const void* txt, int T, int H, int W, int txt_len, void* out,
+                            void* ext_ws, size_t ext_ws_bytes, void* stream) {
   if (!e || !vid || !txt || !out) return set_error(SVR2_ERR_ARG, "svr2_dit_forward: null argument");
   if (T <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || txt_len <= 0)
     return fail(e, SVR2_ERR_ARG, "svr2_dit_forward: T, H, W > 0, H and W even, txt_len > 0");
@@ -482,7 +499,9 @@ extern "C" int svr2_dit_forward(svr2_t* e, const void* vid, const void* txt, int
   const int max_total = g->lay[0].total > g->lay[1].total ? g->lay[0].total : g->lay[1].total;
   const int max_win = g->lay[0].n_win > g->lay[1].n_win ? g->lay[0].n_win : g->lay[1].n_win;
   const Plan P = make_plan(D, T, H, W, l, max_total, L + max_win * l, fuse);
-  if (P.total > e->workspace_bytes) {
+  if (ext_ws) {
+    if (ext_ws_bytes < P.total) return fail(e, SVR2_ERR_ARG, "svr2_dit_forward_ws: workspace smaller than svr2_workspace_bytes()");
+  } else if (P.total > e->workspace_bytes) {
     // grow: the outgrown block is kept until svr2_destroy — work already queued, or a captured CUDA graph of a smaller
     // geometry, may still use it (freeing it would hand its address to someone else)
     if (e->workspace) e->retired_workspaces.push_back(e->workspace);
@@ -491,7 +510,7 @@ extern "C" int svr2_dit_forward(svr2_t* e, const void* vid, const void* txt, int
     if (cudaMalloc(&e->workspace, P.total) != cudaSuccess) return fail(e, SVR2_ERR_CUDA, "svr2_dit_forward: workspace allocation failed");
     e->workspace_bytes = P.total;
   }
-  char* ws = reinterpret_cast<char*>(e->workspace);
+  char* ws = reinterpret_cast<char*>(ext_ws ? ext_ws : e->workspace);
   auto B = [&](size_t off) { return reinterpret_cast<void*>(ws + off); };
   char name[96];
   auto Wt = [&](const char* fmt, int i, const char* s, const char* n) -> const void* {

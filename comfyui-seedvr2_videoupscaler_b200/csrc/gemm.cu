@@ -569,8 +569,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_STRIDE;
 
       float row_lse = 0.f;
-      float st_mx = -INFINITY, st_sum = 0.f;       // KIND_PEXP with stat2: this thread's (row, column slot) statistics
-      float st_mx1 = -INFINITY, st_sum1 = 0.f;     // (second chain)
+      float2 st_a = make_float2(0.f, 0.f), st_b = make_float2(0.f, 0.f);   // KIND_PEXP_STAT: this thread's row sum
       if constexpr (IS_PEXP) {
         const int m = m_blk * BLOCK_M + row;
         row_lse = (m < p.M) ? gate[m] : 0.f;
@@ -746,14 +745,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               if constexpr (IS_PEXP) {
                 const float ea = exp2_approx(fmaf(a, sc, -row_lse)), eb = exp2_approx(fmaf(b, sc, -row_lse));
                 pk[i] = pack_bf16x2(ea, eb);
-                if constexpr (want_stats) {
-                  if (stats_full) {                 // interior phase: two independent chains, no column tests
-                    if (i & 1) { st_sum1 += ea + eb; st_mx1 = fmaxf(fmaxf(st_mx1, a), b); }
-                    else { st_sum += ea + eb; st_mx = fmaxf(fmaxf(st_mx, a), b); }
+                if constexpr (want_stats) {         // fp32 row sum of the exponentials (two packed chains)
+                  if (stats_full) {
+                    if (i & 1) st_b = fadd2(st_b, make_float2(ea, eb));
+                    else st_a = fadd2(st_a, make_float2(ea, eb));
                   } else {                          // last n-tile: columns past N are zero-padded operands, not scores
                     const int cn = n_base + ph0 + 2 * i;
-                    if (cn < p.N) { st_sum += ea; st_mx = fmaxf(st_mx, a); }
-                    if (cn + 1 < p.N) { st_sum += eb; st_mx = fmaxf(st_mx, b); }
+                    if (cn < p.N) st_a.x += ea;
+                    if (cn + 1 < p.N) st_a.y += eb;
                   }
                 }
               } else {
@@ -964,7 +963,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int m = m_blk * BLOCK_M + row;
             if (m < p.M && !(TWO && m_blk >= p.num_m_tiles)) {
               const int slot = (N_COLS >= 64) ? n_blk * 2 + half : n_blk;
-              p.stat2[(long long)m * p.ld_stat + slot] = make_float2(fmaxf(st_mx, st_mx1) * p.out_scale, st_sum + st_sum1);
+              p.stat2[(long long)m * p.ld_stat + slot] = make_float2(0.f, (st_a.x + st_b.x) + (st_a.y + st_b.y));
             }
           }
         }

@@ -378,8 +378,11 @@ class B200NaDiT(EngineModule):
         txt = txt.to(dev, torch.bfloat16).contiguous()
         if self.native and lib.PROFILER is None and self.fuse_qkv == (cfg["heads"] % 2 == 0):
             out = torch.empty(T * H * Wd, cfg["out_ch"], device=dev, dtype=torch.bfloat16)
-            lib.call("svr2_dit_forward", self.native_handle(), lib.ptr(vid), lib.ptr(txt), T, H, Wd, l, lib.ptr(out),
-                     lib.stream())
+            # the workspace comes from torch's caching allocator (and from the capture pool inside a CUDA graph) and goes
+            # back to it after the forward: the VAE phases need those bytes (35 GB at a 65-frame 4K clip)
+            ws = torch.empty(self.workspace_bytes(T, H, Wd, l), device=dev, dtype=torch.uint8)
+            lib.call("svr2_dit_forward_ws", self.native_handle(), lib.ptr(vid), lib.ptr(txt), T, H, Wd, l, lib.ptr(out),
+                     lib.ptr(ws), ws.numel(), lib.stream())
             n_l = cfg["layers"]
             lib.LAUNCHES += 15 * n_l - (3 if cfg["last_vid_only"] else 0) + 5 + (1 if cfg["out_norm"] else 0) - 1
             return NaDiTOutput(out)

@@ -40,6 +40,7 @@ SIGNATURES = {
     "svr2_load_weights": [_P, POINTER(TensorDesc), ctypes.c_size_t, c_int],
     "svr2_workspace_bytes": [_P, c_int, c_int, c_int, c_int],
     "svr2_dit_forward": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
+    "svr2_dit_forward_ws": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, ctypes.c_size_t, _P],
     "svr2_linear_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, c_float, _P],
     "svr2_conv3d_bf16": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_int, _P, _P, _P, c_int, c_int, c_int, _P],

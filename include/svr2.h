@@ -91,6 +91,10 @@ size_t svr2_workspace_bytes(svr2_t* engine, int T, int H, int W, int txt_len);
  * first call for a geometry builds its index tables (synchronous uploads) and may grow the workspace. */
 int svr2_dit_forward(svr2_t* engine, const void* vid, const void* txt, int T, int H, int W, int txt_len, void* out,
                      void* stream);
+/* the same forward in a caller-provided workspace (>= svr2_workspace_bytes, 256-byte aligned): the engine allocates and
+ * retains nothing, so hosts that pool device memory (PyTorch's allocator, a CUDA-graph capture) keep control of it */
+int svr2_dit_forward_ws(svr2_t* engine, const void* vid, const void* txt, int T, int H, int W, int txt_len, void* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K1: Linear.  out[M,N] = epi(a[M,K] @ w[N,K]^T).  Replaces nn.Linear at
  * dit_3b/nablocks/attention/mmattn.py:56-59,173,269; dit_3b/mlp.py:56-61; dit_7b/mlp.py:35-43;
