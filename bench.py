@@ -27,7 +27,12 @@ import sys
 import threading
 import time
 
-import torch
+# Clips that fill the HBM (temporally sliced VAE passes sized from the free memory) need an allocator that does not
+# fragment: expandable segments, chosen before torch initialises CUDA.  The default workloads keep torch's default.
+if any(("4k_clip64" in a or "vae_decode" in a) for a in sys.argv):
+    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

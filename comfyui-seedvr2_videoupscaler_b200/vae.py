@@ -377,11 +377,17 @@ class B200VideoVAE(EngineModule):
             return fn(src)
         outs = []
         key = (fn.__name__, tuple(src.shape), tuple(cuts))
-        if key not in self._sliced_plans and not torch.cuda.is_current_stream_capturing():
+        if not torch.cuda.is_current_stream_capturing():
             # long clips run close to the HBM limit: the FIRST sliced pass of a shape starts from an unfragmented pool.
-            # Repeats of the same shape find their blocks in the caching allocator (same allocation sequence), and
-            # emptying it again would put a synchronous cudaMalloc in front of every layer (measured: 5 % idle at 3')
-            torch.cuda.empty_cache()
+            # Repeats of the same shape find their blocks in the caching allocator; the cache is emptied again only when
+            # it holds a large share of the device un-allocated (fragmentation risk) and the allocator is not the
+            # non-fragmenting one (PYTORCH_CUDA_ALLOC_CONF=expandable_segments:True, which bench.py selects for these
+            # workloads) — every empty_cache puts synchronous cudaFree / cudaMalloc calls in front of the layers.
+            expandable = "expandable_segments:True" in os.environ.get("PYTORCH_CUDA_ALLOC_CONF", "")
+            idle = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+            total = torch.cuda.get_device_properties(self.device).total_memory
+            if key not in self._sliced_plans or (not expandable and idle > 0.25 * total):
+                torch.cuda.empty_cache()
             self._sliced_plans.add(key)
         self._chunk = {"first": True, "state": {}}
         try:
