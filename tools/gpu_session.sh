@@ -22,6 +22,9 @@ for s in $STAGES; do
     debug_native) timeout 300 python tools/debug_native.py > gpurun_out/r2_debug_native.log 2>&1; cat gpurun_out/r2_debug_native.log | tail -14 ;;
     tests_attn) timeout 600 python -m pytest tests -m gpu -q -k "attn or attention or dit_vs_golden or native" > gpurun_out/r2_pytest_attn.log 2>&1; tail -8 gpurun_out/r2_pytest_attn.log ;;
     ab_upsample) for v in "" NO_RUNIF NO_ROWSCALE NO_BOTH; do for i in 1 2 3; do if [ -z "$v" ]; then L=""; else L="$PWD/comfyui-seedvr2_videoupscaler_b200/csrc/libsvr2_ab_$v.so"; fi; echo -n "lib=${v:-default} "; SVR2_LIB=$L python tools/perf_conv_one.py upsample 2>&1 | tail -1; done; done | tee gpurun_out/r2_ab_upsample.log ;;
+    mgpu8)    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
+              timeout 900 $TR bench.py --gpus 8 --workload 4k_shard_7b --steps 3 --warmup 2 --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_4k_shard_7b_n8.json 2> gpurun_out/r2_bench_4k_shard_7b_n8.err; cut -c1-400 gpurun_out/r2_bench_4k_shard_7b_n8.json
+              for T in 16 128; do timeout 900 $TR bench.py --gpus 8 --workload vae_decode_T$T --steps 2 --warmup 1 --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_vae_decode_T${T}_n8.json 2> gpurun_out/r2_bench_vae_decode_T${T}_n8.err; cut -c1-330 gpurun_out/r2_bench_vae_decode_T${T}_n8.json; echo; done ;;
     *) echo "unknown stage $s" ;;
   esac
 done
