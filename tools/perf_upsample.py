@@ -26,3 +26,13 @@ for name, (T, H, W, C, temporal) in {"up0 512ch 3x270x480 (t+s)": (3, 270, 480, 
     flops = 2.0 * T * H * W * C * 4 * z * C
     print(f"{name:32s} {ms:7.3f} ms  write {gb_w:6.2f} GB  read {gb_r:5.2f} GB  {(gb_w + gb_r) / ms:6.2f} TB/s  {flops / ms / 1e9:7.1f} TFLOP/s", flush=True)
     del x, y
+# reference points: pure write (memset / fill) and read+write copy of a buffer of up2's size
+y = torch.empty(11, 2160, 3840, 256, device=dev, dtype=torch.bfloat16)
+x2 = torch.empty_like(y)
+for name, fn, nbytes in (("memset (zero_)", lambda: y.zero_(), y.numel() * 2), ("fill_(1)", lambda: y.fill_(1.0), y.numel() * 2),
+                         ("copy_ (read+write)", lambda: y.copy_(x2), 2 * y.numel() * 2)):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+    print(f"{name:32s} {e0.elapsed_time(e1):7.3f} ms  {nbytes / 1e9:6.2f} GB  {nbytes / e0.elapsed_time(e1) / 1e9:6.2f} TB/s", flush=True)
