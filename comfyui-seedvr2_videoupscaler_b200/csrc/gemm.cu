@@ -174,10 +174,10 @@ struct RowDest {
 };
 
 template <int BLOCK_N>
-__device__ __forceinline__ RowDest row_dest(const GemmParams& p, int m_blk, int n_blk, int row, int n_cols) {
+__device__ __forceinline__ RowDest row_dest(const GemmParams& p, int epi, int m_blk, int n_blk, int row, int n_cols) {
   RowDest d;
   d.dup = 0;
-  if (p.epi & EPI_SHUFFLE) {
+  if (epi & EPI_SHUFFLE) {
     const int m = m_blk * BLOCK_M + row;
     d.valid = m < p.M;
     const int hw = p.shuf_H * p.shuf_W;
@@ -219,7 +219,10 @@ __device__ __forceinline__ RowDest row_dest(const GemmParams& p, int m_blk, int 
 // TWO: a cluster of 2 CTAs (one SM pair) works on a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2:
 // each CTA loads its own 128 A rows and half of the B rows, CTA 0 issues the MMAs for both, each CTA
 // drains its own 128 x BLOCK_N accumulator.  Halves the B traffic per SM and the per-SM smem read rate.
-template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false>
+// EPI_CT >= 0: the epilogue flags are a compile-time constant (p.epi must equal it) — the per-element loops then carry
+// no runtime flag tests.  A single such test cost the short-K pixel-shuffle GEMM 50 % (its epilogue, ~1 800 warp
+// instructions per tile, is the whole kernel); EPI_CT = -1 keeps the generic runtime-flag epilogue.
+template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false, int EPI_CT = -1>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a2, const GemmParams p) {
@@ -450,7 +453,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const bool active = (N_COLS >= 64) || (half == 0);
     const int col_lo = (N_COLS >= 64) ? half * COLS_W : 0;
     uint8_t* slab = smem + L::kStagingOffset + (warp - 4) * 4096;
-    const int epi = p.epi;
+    const int epi = EPI_CT >= 0 ? EPI_CT : p.epi;
     const int n_lim = KIND == KIND_SWIGLU ? p.N / 2 : p.N;
     const __nv_bfloat16* __restrict__ bias = p.bias;
     const float* __restrict__ gate = p.gate;
@@ -543,7 +546,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
-      RowDest dst = row_dest<BLOCK_N>(p, m_blk, n_blk, row, N_COLS);
+      RowDest dst = row_dest<BLOCK_N>(p, epi, m_blk, n_blk, row, N_COLS);
       if (TWO && m_blk >= p.num_m_tiles) { dst.valid = 0; dst.dup = 0; }
       const int n_base = n_blk * (KIND == KIND_SWIGLU ? BLOCK_N / 2 : BLOCK_N);   // first output column
 
@@ -1042,12 +1045,12 @@ int num_sms() {
   return g_num_sms[dev];
 }
 
-template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false>
+template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false, int EPI_CT = -1>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, cudaStream_t stream,
                        const CUtensorMap* ta2_opt = nullptr) {
   const CUtensorMap& ta2 = ta2_opt ? *ta2_opt : ta;
   using L = SmemLayout<BLOCK_N, TWO>;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, KIND, SWAP, TWO>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, KIND, SWAP, TWO, EPI_CT>;
   GemmParams p = p_in;
   {
     // raster group: keep the group's B slice around 24 MB (L2 = 126 MB, shared with A tiles and the output stream)
@@ -1138,6 +1141,13 @@ static int dispatch_gemm(int block_n, const CUtensorMap& ta, const CUtensorMap& 
     if (p.epi & EPI_ROWSTAT) return launch_gemm<256, KIND_ROWSTAT, false, true>(ta, tb, p, s);
     if (p.epi & EPI_PEXP) return launch_gemm<256, KIND_PEXP, false, true>(ta, tb, p, s);
     if (p.epi & EPI_F32) return launch_gemm<256, KIND_F32, false, true>(ta, tb, p, s);
+    switch (p.epi) {      // the epilogue-bound shapes of the hot path get flag-free epilogues
+      case EPI_SHUFFLE | EPI_BIAS: return launch_gemm<256, KIND_BF16, false, true, EPI_SHUFFLE | EPI_BIAS>(ta, tb, p, s);
+      case EPI_BIAS | EPI_GATE | EPI_RESIDUAL: return launch_gemm<256, KIND_BF16, false, true, EPI_BIAS | EPI_GATE | EPI_RESIDUAL>(ta, tb, p, s);
+      case EPI_GATE | EPI_RESIDUAL: return launch_gemm<256, KIND_BF16, false, true, EPI_GATE | EPI_RESIDUAL>(ta, tb, p, s);
+      case EPI_BIAS: return launch_gemm<256, KIND_BF16, false, true, EPI_BIAS>(ta, tb, p, s);
+      case 0: return launch_gemm<256, KIND_BF16, false, true, 0>(ta, tb, p, s);
+    }
     return launch_gemm<256, KIND_BF16, false, true>(ta, tb, p, s);
   }
   if (p.epi & EPI_SWIGLU) {
