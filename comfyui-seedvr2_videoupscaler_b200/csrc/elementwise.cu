@@ -517,9 +517,10 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
 // Same arithmetic, leaner: the bf16 rounding of the normalised value is one cvt.rn.bf16x2 per channel pair (instead
 // of an integer round-to-nearest-even per value), six 16-byte loads in flight per thread and at most 64 registers
 // so that four blocks fit an SM — the kernel is latency-bound at the power-capped clock, not DRAM-bound.
+template <bool SILU>
 __global__ void __launch_bounds__(256, 4) groupnorm_apply_v2_kernel(const __nv_bfloat16* __restrict__ x,
                                                                     __nv_bfloat16* __restrict__ y, int hw, int C,
-                                                                    int silu, int out_t_pad, int out_dup_head,
+                                                                    int out_t_pad, int out_dup_head,
                                                                     const float2* __restrict__ coef) {
   const int f = blockIdx.y;
   const int cvec = C / 8;
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(256, 4) groupnorm_apply_v2_kernel(const __nv_b
       const float t0 = fmaf(__uint_as_float(w[e] << 16), ca[2 * e], cb[2 * e]);
       const float t1 = fmaf(__uint_as_float(w[e] & 0xffff0000u), ca[2 * e + 1], cb[2 * e + 1]);
       uint32_t pk = pack_bf16x2(t0, t1);              // F.group_norm output is bf16
-      if (silu) pk = pack_bf16x2(silu_fast(__uint_as_float(pk << 16)), silu_fast(__uint_as_float(pk & 0xffff0000u)));
+      if constexpr (SILU) pk = pack_bf16x2(silu_fast(__uint_as_float(pk << 16)), silu_fast(__uint_as_float(pk & 0xffff0000u)));
       o[e] = pk;
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
@@ -590,8 +591,12 @@ static void launch_gn_apply(const void* x, void* y, int frames, int hw, int C, i
   if (gn_apply_v2()) {
     int bx = (int)((nvec + 256 * 12 - 1) / (256 * 12));
     if (bx < 1) bx = 1;
-    groupnorm_apply_v2_kernel<<<dim3(bx, frames), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, C, silu,
-                                                               out_t_pad, out_dup_head, coef);
+    if (silu)
+      groupnorm_apply_v2_kernel<true><<<dim3(bx, frames), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, C,
+                                                                       out_t_pad, out_dup_head, coef);
+    else
+      groupnorm_apply_v2_kernel<false><<<dim3(bx, frames), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, C,
+                                                                        out_t_pad, out_dup_head, coef);
   } else {
     int bx = (int)((nvec + 256 * 8 - 1) / (256 * 8));
     if (bx < 1) bx = 1;

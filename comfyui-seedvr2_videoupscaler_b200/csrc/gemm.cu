@@ -26,6 +26,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 #include "svr2_internal.h"
 
@@ -741,6 +743,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             constexpr bool want_stats = KIND == KIND_PEXP_STAT;
             const bool stats_full = n_base + ph0 + 64 <= p.N;
             const bool plain = !(epi & (EPI_GELU | EPI_SILU | EPI_GATE));
+            auto elements = [&](auto ragged) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               float a = __uint_as_float(i < 16 ? v0[2 * (i & 15)] : v1[2 * (i & 15)]);
@@ -749,13 +752,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const float ea = exp2_approx(fmaf(a, sc, -row_lse)), eb = exp2_approx(fmaf(b, sc, -row_lse));
                 pk[i] = pack_bf16x2(ea, eb);
                 if constexpr (want_stats) {         // fp32 row sum of the exponentials (two packed chains)
-                  if (stats_full) {
-                    if (i & 1) st_b = fadd2(st_b, make_float2(ea, eb));
-                    else st_a = fadd2(st_a, make_float2(ea, eb));
-                  } else {                          // last n-tile: columns past N are zero-padded operands, not scores
+                  if constexpr (decltype(ragged)::value) {   // last n-tile: zero-padded operand columns are not scores
                     const int cn = n_base + ph0 + 2 * i;
                     if (cn < p.N) st_a.x += ea;
                     if (cn + 1 < p.N) st_a.y += eb;
+                  } else {
+                    if (i & 1) st_b = fadd2(st_b, make_float2(ea, eb));
+                    else st_a = fadd2(st_a, make_float2(ea, eb));
                   }
                 }
               } else {
@@ -785,6 +788,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 pk[i] = r;
               }
             }
+            };
+            if (want_stats && !stats_full) elements(std::true_type{});
+            else elements(std::false_type{});
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               *reinterpret_cast<uint4*>(slab + lane * 128 + ((c ^ (lane & 7)) << 4)) =
