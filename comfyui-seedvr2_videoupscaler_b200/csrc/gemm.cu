@@ -749,7 +749,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               float a = __uint_as_float(i < 16 ? v0[2 * (i & 15)] : v1[2 * (i & 15)]);
               float b = __uint_as_float(i < 16 ? v0[2 * (i & 15) + 1] : v1[2 * (i & 15) + 1]);
               if constexpr (IS_PEXP) {
-                const float ea = exp2_approx(fmaf(a, sc, -row_lse)), eb = exp2_approx(fmaf(b, sc, -row_lse));
+                // two of every five column pairs take their exp2 on the FMA pipe: the epilogue is MUFU-bound (128 ex2 per
+                // thread and tile = 2048 SM cycles against 1024 of MMA at K = 512)
+                const bool kPoly = (KIND == KIND_PEXP_STAT) && ((i % 5 == 1) || (i % 5 == 3));   // folds after unrolling
+                const float xa = fmaf(a, sc, -row_lse), xb = fmaf(b, sc, -row_lse);
+                const float ea = kPoly ? exp2_poly(xa) : exp2_approx(xa), eb = kPoly ? exp2_poly(xb) : exp2_approx(xb);
                 pk[i] = pack_bf16x2(ea, eb);
                 if constexpr (want_stats) {         // fp32 row sum of the exponentials (two packed chains)
                   if constexpr (decltype(ragged)::value) {   // last n-tile: zero-padded operand columns are not scores

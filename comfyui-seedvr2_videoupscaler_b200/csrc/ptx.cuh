@@ -307,6 +307,20 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
       : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
   return d;
 }
+// exp2 on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f with the round-to-nearest magic-number trick,
+// degree-4 polynomial for 2^f on [-0.5, 0.5] (relative error < 5e-5, far below the bf16 rounding of the probabilities it
+// feeds), exponent inserted with an integer add.  Valid for x in [-125, 127]; smaller x is clamped (result ~2^-125).
+// The MUFU pipe issues 16 ex2 per SM and clock — the bound of the exponent-heavy epilogues — while the FMA pipe idles.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                    // 1.5 * 2^23
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
+  p = fmaf(p, f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 // relative-accuracy forms (tanh.approx would lose the tiny negative tails to cancellation):
 //   silu(x) = x / (1 + e^-x);   gelu_tanh(x) = 0.5 x (1 + tanh u) = x / (1 + e^-2u),  u = k0 (x + k1 x^3)
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
