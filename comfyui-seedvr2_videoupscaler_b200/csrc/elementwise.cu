@@ -716,7 +716,7 @@ template <> __device__ __forceinline__ float ld_as_float<__half>(const __half* p
 
 // in: [C,T,H,W] -> out: [out_t_pad + T, H, W, C_pad] (channels >= C zero), frame 0 duplicated into the halo
 template <typename TIn>
-__global__ void ncdhw_to_ndhwc_kernel(const TIn* __restrict__ in, int C, int T, int H, int W,
+__global__ void ncdhw_to_ndhwc_kernel(const TIn* __restrict__ in, int C, int T, int H, int W, long long chan_stride,
                                       __nv_bfloat16* __restrict__ out, int C_pad, int out_t_pad, float div) {
   const long long hw = (long long)H * W;
   const long long total = (long long)T * hw;
@@ -724,7 +724,7 @@ __global__ void ncdhw_to_ndhwc_kernel(const TIn* __restrict__ in, int C, int T, 
        i += (long long)gridDim.x * blockDim.x) {
     const long long t = i / hw, pix = i % hw;
     for (int c = 0; c < C_pad; ++c) {
-      const float v = c < C ? bf16_round(ld_as_float<TIn>(in, ((long long)c * T + t) * hw + pix)) / div : 0.f;
+      const float v = c < C ? bf16_round(ld_as_float<TIn>(in, (long long)c * chan_stride + t * hw + pix)) / div : 0.f;
       const __nv_bfloat16 b = __float2bfloat16_rn(v);
       out[((t + out_t_pad) * hw + pix) * C_pad + c] = b;
       if (t == 0)
@@ -735,15 +735,15 @@ __global__ void ncdhw_to_ndhwc_kernel(const TIn* __restrict__ in, int C, int T, 
 // in: [T,H,W,ld_in] -> out [C,T,H,W] (first C channels)
 template <typename TOut>
 __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int C, int T, int H, int W,
-                                      TOut* __restrict__ out) {
+                                      TOut* __restrict__ out, long long chan_stride) {
   const long long hw = (long long)H * W, total = (long long)T * hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long t = i / hw, pix = i % hw;
     for (int c = 0; c < C; ++c) {
       const float v = __bfloat162float(in[i * ld_in + c]);
-      if constexpr (sizeof(TOut) == 4) out[((long long)c * T + t) * hw + pix] = v;
-      else out[((long long)c * T + t) * hw + pix] = __float2bfloat16_rn(v);
+      if constexpr (sizeof(TOut) == 4) out[(long long)c * chan_stride + t * hw + pix] = v;
+      else out[(long long)c * chan_stride + t * hw + pix] = __float2bfloat16_rn(v);
     }
   }
 }
@@ -824,7 +824,7 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const __nv_bfloat16* __res
 template <typename TOut>
 __global__ void __launch_bounds__(256) conv_tap_gather_kernel(const float* __restrict__ z, long long ldz, int co_n,
                                                               const __nv_bfloat16* __restrict__ bias, int T, int H, int W,
-                                                              TOut* __restrict__ out) {
+                                                              TOut* __restrict__ out, long long chan_stride) {
   const long long hw = (long long)H * W, total = (long long)T * hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -848,8 +848,8 @@ __global__ void __launch_bounds__(256) conv_tap_gather_kernel(const float* __res
       }
     for (int c = 0; c < co_n; ++c) {
       const float v = bf16_round(acc[c] + __bfloat162float(bias[c]));
-      if constexpr (sizeof(TOut) == 4) out[(long long)c * total + i] = v;
-      else out[(long long)c * total + i] = __float2bfloat16_rn(v);
+      if constexpr (sizeof(TOut) == 4) out[(long long)c * chan_stride + i] = v;
+      else out[(long long)c * chan_stride + i] = __float2bfloat16_rn(v);
     }
   }
 }
@@ -1029,28 +1029,39 @@ extern "C" int svr2_transpose_bf16(const void* in, int64_t ld_in, void* out, int
   return check_launch("transpose");
 }
 
-extern "C" int svr2_ncdhw_to_ndhwc_bf16(const void* in, int in_dtype, int C, int T, int H, int W, void* out, int C_pad,
-                                        int out_t_pad, float div, void* stream) {
+// channel stride of the NCDHW side in elements (T*H*W for a contiguous tensor; larger for a temporal slice of a clip)
+int svr2::ncdhw_to_ndhwc_strided(const void* in, int in_dtype, int C, int T, int H, int W, int64_t chan_stride, void* out,
+                                 int C_pad, int out_t_pad, float div, void* stream) {
   const long long total = (long long)T * H * W;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t s = (cudaStream_t)stream;
-  if (in_dtype == 0) ncdhw_to_ndhwc_kernel<float><<<blocks, 256, 0, s>>>((const float*)in, C, T, H, W, (__nv_bfloat16*)out, C_pad, out_t_pad, div);
-  else if (in_dtype == 1) ncdhw_to_ndhwc_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, C, T, H, W, (__nv_bfloat16*)out, C_pad, out_t_pad, div);
-  else if (in_dtype == 2) ncdhw_to_ndhwc_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)in, C, T, H, W, (__nv_bfloat16*)out, C_pad, out_t_pad, div);
+  const long long cs = chan_stride;
+  if (in_dtype == 0) ncdhw_to_ndhwc_kernel<float><<<blocks, 256, 0, s>>>((const float*)in, C, T, H, W, cs, (__nv_bfloat16*)out, C_pad, out_t_pad, div);
+  else if (in_dtype == 1) ncdhw_to_ndhwc_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, C, T, H, W, cs, (__nv_bfloat16*)out, C_pad, out_t_pad, div);
+  else if (in_dtype == 2) ncdhw_to_ndhwc_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)in, C, T, H, W, cs, (__nv_bfloat16*)out, C_pad, out_t_pad, div);
   else return set_error(SVR2_ERR_ARG, "ncdhw_to_ndhwc: dtype must be 0 (f32), 1 (bf16) or 2 (f16)");
   return check_launch("ncdhw_to_ndhwc");
 }
-extern "C" int svr2_ndhwc_to_ncdhw(const void* in, int ld_in, int C, int T, int H, int W, void* out, int out_dtype,
-                                   void* stream) {
+extern "C" int svr2_ncdhw_to_ndhwc_bf16(const void* in, int in_dtype, int C, int T, int H, int W, void* out, int C_pad,
+                                        int out_t_pad, float div, void* stream) {
+  return ncdhw_to_ndhwc_strided(in, in_dtype, C, T, H, W, (int64_t)T * H * W, out, C_pad, out_t_pad, div, stream);
+}
+int svr2::ndhwc_to_ncdhw_strided(const void* in, int ld_in, int C, int T, int H, int W, void* out, int out_dtype,
+                                 int64_t chan_stride, void* stream) {
   const long long total = (long long)T * H * W;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t s = (cudaStream_t)stream;
-  if (out_dtype == 0) ndhwc_to_ncdhw_kernel<float><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, ld_in, C, T, H, W, (float*)out);
-  else if (out_dtype == 1) ndhwc_to_ncdhw_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, ld_in, C, T, H, W, (__nv_bfloat16*)out);
+  const long long cs = chan_stride;
+  if (out_dtype == 0) ndhwc_to_ncdhw_kernel<float><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, ld_in, C, T, H, W, (float*)out, cs);
+  else if (out_dtype == 1) ndhwc_to_ncdhw_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)in, ld_in, C, T, H, W, (__nv_bfloat16*)out, cs);
   else return set_error(SVR2_ERR_ARG, "ndhwc_to_ncdhw: dtype must be 0 (f32) or 1 (bf16)");
   return check_launch("ndhwc_to_ncdhw");
+}
+extern "C" int svr2_ndhwc_to_ncdhw(const void* in, int ld_in, int C, int T, int H, int W, void* out, int out_dtype,
+                                   void* stream) {
+  return ndhwc_to_ncdhw_strided(in, ld_in, C, T, H, W, out, out_dtype, (int64_t)T * H * W, stream);
 }
 extern "C" int svr2_im2col3_bf16(const void* x, int T, int H, int W, int C, int ld_in, void* out, int ld_out,
                                  void* stream) {
@@ -1067,18 +1078,24 @@ extern "C" int svr2_im2col3_bf16(const void* x, int T, int H, int W, int C, int 
   return check_launch("im2col3");
 }
 
-// z: [27*co_n rows][ldz] fp32 (row = tap*co_n + co, column = input pixel incl. 2 halo frames); out: [co_n,T,H,W]
-extern "C" int svr2_conv_tap_gather(const float* z, int64_t ldz, int co_n, const void* bias, int T, int H, int W,
-                                    void* out, int out_dtype, void* stream) {
+// z: [27*co_n rows][ldz] fp32 (row = tap*co_n + co, column = input pixel incl. 2 halo frames); out: [co_n,T,H,W] with
+// channel stride chan_stride elements
+int svr2::conv_tap_gather_strided(const float* z, int64_t ldz, int co_n, const void* bias, int T, int H, int W, void* out,
+                                  int out_dtype, int64_t chan_stride, void* stream) {
   if (co_n < 1 || co_n > 4) return set_error(SVR2_ERR_ARG, "conv_tap_gather: 1 <= co_n <= 4");
   const long long total = (long long)T * H * W;
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   cudaStream_t s = (cudaStream_t)stream;
+  const long long cs = chan_stride;
   if (out_dtype == 0)
-    conv_tap_gather_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(z, ldz, co_n, (const __nv_bfloat16*)bias, T, H, W, (float*)out);
+    conv_tap_gather_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(z, ldz, co_n, (const __nv_bfloat16*)bias, T, H, W, (float*)out, cs);
   else if (out_dtype == 1)
-    conv_tap_gather_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(z, ldz, co_n, (const __nv_bfloat16*)bias, T, H, W, (__nv_bfloat16*)out);
+    conv_tap_gather_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(z, ldz, co_n, (const __nv_bfloat16*)bias, T, H, W, (__nv_bfloat16*)out, cs);
   else return set_error(SVR2_ERR_ARG, "conv_tap_gather: dtype must be 0 (f32) or 1 (bf16)");
   return check_launch("conv_tap_gather");
+}
+extern "C" int svr2_conv_tap_gather(const float* z, int64_t ldz, int co_n, const void* bias, int T, int H, int W,
+                                    void* out, int out_dtype, void* stream) {
+  return conv_tap_gather_strided(z, ldz, co_n, bias, T, H, W, out, out_dtype, (int64_t)T * H * W, stream);
 }

@@ -20,26 +20,9 @@
 #include <unordered_map>
 #include <vector>
 
-#include "svr2_internal.h"
+#include "engine_internal.h"
 
 namespace svr2 {
-namespace {
-
-struct Tensor {
-  void* ptr = nullptr;
-  int dtype = 1;          // 0 f32, 1 bf16, 2 f16
-  int rank = 0;
-  int64_t shape[5] = {0, 0, 0, 0, 0};
-  bool owned = false;
-  int64_t numel() const {
-    int64_t n = 1;
-    for (int i = 0; i < rank; ++i) n *= shape[i];
-    return n;
-  }
-};
-
-inline size_t dtype_size(int dt) { return dt == 0 ? 4 : 2; }
-inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // One window layout (regular or shifted) of a clip geometry, device-resident index tables.
 struct Layout {
@@ -58,6 +41,8 @@ struct Geometry {
   int nfreq = 0;
   std::vector<void*> allocs;
 };
+
+namespace {
 
 struct Box {
   int t0, t1, h0, h1, w0, w1;
@@ -119,29 +104,9 @@ inline float round_to(float x, int dtype) {
 
 using namespace svr2;
 
-struct svr2_engine {
-  int device = 0;
-  svr2_model_desc desc{};
-  std::unordered_map<std::string, Tensor> w;
-  std::map<std::vector<int>, Geometry*> geo;      // (T, Hp, Wp, l) -> tables
-  void* workspace = nullptr;
-  size_t workspace_bytes = 0;
-  std::vector<void*> retired_workspaces;          // outgrown blocks: a captured CUDA graph may still replay into them
-  char err[256] = "";
-};
 
 namespace svr2 {
 namespace {
-
-int fail(svr2_engine* e, int code, const char* msg) {
-  if (e) snprintf(e->err, sizeof e->err, "%s", msg);
-  return set_error(code, msg);
-}
-
-const Tensor* find(svr2_engine* e, const std::string& name) {
-  auto it = e->w.find(name);
-  return it == e->w.end() ? nullptr : &it->second;
-}
 
 template <typename T>
 T* upload(Geometry* g, const std::vector<T>& host) {
@@ -369,9 +334,10 @@ bool fuse_qkv_ok(svr2_engine* e, int nfreq) { return (e->desc.heads % 2 == 0) &&
 // ------------------------------------------------------------------------------------------------------------------
 extern "C" int svr2_create(svr2_t** out, int device, const svr2_model_desc* desc) {
   if (!out || !desc) return set_error(SVR2_ERR_ARG, "svr2_create: null argument");
-  if (desc->heads <= 0 || desc->dim != desc->heads * 128)
+  if (desc->variant < 0 || desc->variant > 2)
+    return set_error(SVR2_ERR_ARG, "svr2_create: variant 0 (NaDiT 3B), 1 (NaDiT 7B) or 2 (video VAE)");
+  if (desc->variant != 2 && (desc->heads <= 0 || desc->dim != desc->heads * 128))
     return set_error(SVR2_ERR_ARG, "svr2_create: dim must equal heads * 128 (head_dim 128)");
-  if (desc->variant != 0 && desc->variant != 1) return set_error(SVR2_ERR_ARG, "svr2_create: variant 0 (3B) or 1 (7B)");
   int cur = 0;
   cudaGetDevice(&cur);
   if (cudaSetDevice(device) != cudaSuccess) return set_error(SVR2_ERR_CUDA, "svr2_create: cudaSetDevice failed");
@@ -396,6 +362,7 @@ extern "C" void svr2_destroy(svr2_t* e) {
   }
   if (e->workspace) cudaFree(e->workspace);
   for (void* p : e->retired_workspaces) cudaFree(p);
+  vae_state_destroy(e);
   delete e;
 }
 
@@ -448,7 +415,7 @@ extern "C" int svr2_load_weights(svr2_t* e, const svr2_tensor_desc* tensors, siz
 
 // bytes of engine-owned workspace one svr2_dit_forward of this geometry uses (allocated / grown on first use)
 extern "C" size_t svr2_workspace_bytes(svr2_t* e, int T, int H, int W, int txt_len) {
-  if (!e || T <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || txt_len <= 0) return 0;
+  if (!e || e->desc.variant == 2 || T <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || txt_len <= 0) return 0;
   const int Hp = H / 2, Wp = W / 2;
   size_t max_total = 0, max_win = 0;
   for (int s = 0; s < 2; ++s) {
@@ -491,6 +458,7 @@ static int dit_forward_impl(svr2_t* e, const void* vid, const void* txt, int T, 
   cudaGetDevice(&cur);
   if (cur != e->device) return fail(e, SVR2_ERR_ARG, "svr2_dit_forward: the handle's device is not the current device");
   const svr2_model_desc& D = e->desc;
+  if (D.variant == 2) return fail(e, SVR2_ERR_ARG, "svr2_dit_forward: the handle was created as a VAE (variant 2)");
   const int Hp = H / 2, Wp = W / 2, l = txt_len, d = D.dim, heads = D.heads, inner = heads * 128;
   const int L = T * Hp * Wp;
   Geometry* g = geometry(e, T, Hp, Wp, l);

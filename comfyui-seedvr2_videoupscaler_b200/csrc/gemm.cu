@@ -1379,6 +1379,30 @@ extern "C" int svr2_conv3d_shortcut_stats_bf16(const void* x, int T_in_total, in
                      out_t_pad, out_dup_head, Cout, stat_partial, stat_bytes, stat_slots, stream, x2, C2);
 }
 
+// Output tile of the implicit-GEMM conv.  Cout <= 128: swap operands (128 channels x 256 pixels per tile); else
+// 128 pixels x up to 256 channels.  bw x bh output pixels (128, or 256 when swapped).
+static void conv_tile_shape(int Cout, int H_out, int W_out, bool* swap_out, int* bw_out, int* bh_out) {
+  const bool swap = (Cout > 64 && Cout <= 128) && (long long)H_out * W_out >= 256;
+  int bw = 16, bh = 8;
+  if (swap) {
+    bw = 32; bh = 8;
+    if (W_out <= 16) { bw = 16; bh = 16; }
+    if (W_out <= 8) { bw = 8; bh = 32; }
+  } else {
+    if (W_out >= 128 && H_out < 8) { bw = 128; bh = 1; }
+    else if (W_out <= 8) { bw = 8; bh = 16; }
+  }
+  *swap_out = swap; *bw_out = bw; *bh_out = bh;
+}
+// GroupNorm partial-sum slots per frame a conv with statistics writes (the size query of svr2_conv3d_stats_bf16 without
+// the tensor maps: workspace planning)
+extern "C" int svr2_conv_stat_slots(int Cout, int H_out, int W_out) {
+  bool swap;
+  int bw, bh;
+  conv_tile_shape(Cout, H_out, W_out, &swap, &bw, &bh);
+  return ((W_out + bw - 1) / bw) * ((H_out + bh - 1) / bh) * (swap ? 2 : 4);
+}
+
 static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, const void* w, int Cout, int kt,
                        int kh, int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags,
                        const void* bias, const void* residual, void* y, int out_t_pad, int out_dup_head,
@@ -1389,18 +1413,9 @@ static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, con
   if (stride_hw != 1 && stride_hw != 2) return set_error(SVR2_ERR_ARG, "stride_hw must be 1 or 2");
   const int H_out = stride_hw == 1 ? H : H / 2, W_out = stride_hw == 1 ? W : W / 2;
   if (stride_hw == 2 && ((H | W) & 1)) return set_error(SVR2_ERR_ARG, "stride-2 conv needs even H, W");
-  // Cout <= 128: swap operands (128 channels x 256 pixels per tile); else 128 pixels x up to 256 channels
-  const bool swap = (Cout > 64 && Cout <= 128) && (long long)H_out * W_out >= 256;
-  // tile shape: bw x bh output pixels (128, or 256 when swapped)
-  int bw = 16, bh = 8;
-  if (swap) {
-    bw = 32; bh = 8;
-    if (W_out <= 16) { bw = 16; bh = 16; }
-    if (W_out <= 8) { bw = 8; bh = 32; }
-  } else {
-    if (W_out >= 128 && H_out < 8) { bw = 128; bh = 1; }
-    else if (W_out <= 8) { bw = 8; bh = 16; }
-  }
+  bool swap;
+  int bw, bh;
+  conv_tile_shape(Cout, H_out, W_out, &swap, &bw, &bh);
   const int bn = swap ? 128 : pick_block_n(Cout, 0);
   CUtensorMap ta, tb;
   int rc;
@@ -1465,7 +1480,7 @@ static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, con
   p.out = y;
   if (stat_slots_out) {
     if (Cout % 8 || ldc != Cout) return set_error(SVR2_ERR_ARG, "conv stats: need Cout % 8 == 0 and ldc == Cout");
-    const int slots = p.tiles_w * p.tiles_h * (swap ? 2 : 4);
+    const int slots = svr2_conv_stat_slots(Cout, H_out, W_out);
     *stat_slots_out = slots;
     if (!stat_partial) return SVR2_OK;   // size query only
     const int64_t need = (int64_t)T_out * slots * (Cout / 8) * 16;

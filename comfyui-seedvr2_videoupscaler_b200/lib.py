@@ -41,6 +41,10 @@ SIGNATURES = {
     "svr2_workspace_bytes": [_P, c_int, c_int, c_int, c_int],
     "svr2_dit_forward": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P],
     "svr2_dit_forward_ws": [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, ctypes.c_size_t, _P],
+    "svr2_vae_workspace_bytes": [_P, c_int, c_int, c_int, c_int, c_int],
+    "svr2_vae_encode": [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, ctypes.c_size_t, _P],
+    "svr2_vae_decode": [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, ctypes.c_size_t, _P],
+    "svr2_vae_last_launches": [_P],
     "svr2_linear_bf16": [_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, c_float, _P],
     "svr2_conv3d_bf16": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_int, _P, _P, _P, c_int, c_int, c_int, _P],
@@ -48,6 +52,7 @@ SIGNATURES = {
                                c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int64, POINTER(c_int), _P],
     "svr2_conv3d_shortcut_stats_bf16": [_P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int,
                                         _P, c_int, c_int, _P, c_int64, POINTER(c_int), _P],
+    "svr2_conv_stat_slots": [c_int, c_int, c_int],
     "svr2_groupnorm_from_stats_bf16": [_P, _P, c_int, c_int, c_int, _P, _P, c_float, c_int, c_int, c_int, _P, c_int, _P,
                                        _P],
     "svr2_upsample_shuffle_bf16": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_int, c_int, _P],
@@ -112,7 +117,7 @@ def load() -> ctypes.CDLL:
         lib.svr2_engine_last_error.argtypes = [c_void_p]
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
-            fn.restype = c_int64 if name.endswith("_bytes") else (None if name in ("svr2_set_cta_pair", "svr2_destroy") else c_int)
+            fn.restype = c_int64 if (name.endswith("_bytes") or name == "svr2_vae_last_launches") else (None if name in ("svr2_set_cta_pair", "svr2_destroy") else c_int)
             fn.argtypes = args
         _lib = lib
     return _lib

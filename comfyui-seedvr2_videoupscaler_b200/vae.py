@@ -73,6 +73,97 @@ class B200VideoVAE(EngineModule):
         self.split_size = None      # explicit temporal slice length in sample frames (set_causal_slicing)
         self.debug = None           # set by apply_model_specific_config (model_configuration.py:1270-1272)
         self.tensor_offload_device = None
+        # encode / decode sequenced by the native runtime (csrc/vae_engine.cu; default) or by this module's Python
+        # methods (per-call profiling, A/B)
+        self.native = os.environ.get("SVR2_NATIVE_VAE", "1") != "0"
+        self._ws_bytes: Dict[tuple, int] = {}
+
+    # ---- native runtime (csrc/vae_engine.cu): the same sequences in C++ on a svr2_t handle -------------------
+    def _device_state_moved(self):
+        self._drop_handle()
+
+    def _drop_handle(self):
+        h = self.__dict__.get("_handle")
+        if h:
+            lib.engine_destroy(h)
+        self.__dict__["_handle"] = None
+        if "_ws_bytes" in self.__dict__:
+            self._ws_bytes.clear()
+
+    def __del__(self):
+        try:
+            self._drop_handle()
+        except Exception:   # noqa: BLE001 - interpreter shutdown
+            pass
+
+    def native_handle(self):
+        """svr2_t* (variant 2) that borrows this module's weight buffers; conv weights are described with their
+        [Cout, kt, kh, kw, Cin] shape (the buffers are those K-major rows)."""
+        if self.__dict__.get("_handle"):
+            return self._handle
+        h = lib.engine_create(lib.ModelDesc(variant=2), self.device.index if self.device.index is not None
+                              else torch.cuda.current_device())
+        try:
+            lib.engine_load(h, self._native_tensors(), copy=False)
+        except Exception:
+            lib.engine_destroy(h)
+            raise
+        self.__dict__["_handle"] = h
+        return h
+
+    def _native_tensors(self) -> Dict[str, torch.Tensor]:
+        """The weight buffers under their checkpoint names, conv weights viewed as [Cout, kt, kh, kw, Cin]."""
+        tensors = {}
+        for k in self.W.keys():
+            t = self.W[k]
+            if (k + ".k") in self.meta and t.ndim == 2 and k not in ("encoder.conv_in.weight", "decoder.conv_out.weight"):
+                kt, kh, kw = self.meta[k + ".k"]
+                t = t.view(t.shape[0], kt, kh, kw, t.shape[1] // (kt * kh * kw))
+            tensors[k] = t
+        return tensors
+
+    def workspace_bytes(self, encode: bool, T: int, H: int, W: int, slice_frames: int = 0) -> int:
+        """Exact workspace of one native encode (T sample frames of H x W) / decode (T latent frames of H x W latent
+        pixels) with temporal slices of ``slice_frames`` (0 = un-sliced)."""
+        key = (bool(encode), T, H, W, slice_frames)
+        if key not in self._ws_bytes:
+            n = int(lib.load().svr2_vae_workspace_bytes(self.native_handle(), 0 if encode else 1, T, H, W, slice_frames))
+            if n <= 0:
+                raise lib.Svr2Error("svr2_vae_workspace_bytes failed: "
+                                    + lib.load().svr2_engine_last_error(self.native_handle()).decode())
+            self._ws_bytes[key] = n
+        return self._ws_bytes[key]
+
+    def _use_native(self) -> bool:
+        return self.native and lib.PROFILER is None and self.fuse_shortcut and self.single_pass_attention
+
+    def _free_bytes(self) -> int:
+        free, _ = torch.cuda.mem_get_info(self.device)
+        return free + torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+
+    def _native_run(self, encode: bool, src: torch.Tensor, T: int, H: int, W: int, cap, out: torch.Tensor):
+        """Temporal slice length: the largest (un-sliced first, then ``cap`` = set_causal_slicing's split, then halving)
+        whose EXACT workspace fits the free HBM.  The workspace comes from torch's caching allocator (the capture pool
+        inside a CUDA graph) and returns to it after the call."""
+        step = 4 if encode else 1
+        can_slice = not (encode and (T - 1) % 4)       # only 4n+1-frame clips continue the temporal stride phase
+        sz = 0 if (cap is None or T - 1 <= cap or not can_slice) else max(step, cap // step * step)
+        need = self.workspace_bytes(encode, T, H, W, sz)
+        if can_slice and not torch.cuda.is_current_stream_capturing():
+            budget = int(0.92 * self._free_bytes())
+            while need > budget:
+                cur = sz if sz else T - 1
+                nxt = max(step, (cur // 2) // step * step)
+                if nxt >= cur:
+                    break
+                sz = nxt
+                need = self.workspace_bytes(encode, T, H, W, sz)
+        ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[src.dtype]
+        lib.call("svr2_vae_encode" if encode else "svr2_vae_decode", self.native_handle(), lib.ptr(src), dt, T, H, W, sz,
+                 lib.ptr(out), lib.ptr(ws), ws.numel(), lib.stream())
+        lib.LAUNCHES += int(lib.load().svr2_vae_last_launches(self.native_handle())) - 1
+        return out
 
     # ---- weights ---------------------------------------------------------
     def _conv_w(self, w, cin_pad=None, cout_pad=None):
@@ -204,10 +295,7 @@ class B200VideoVAE(EngineModule):
         name, extra = "svr2_conv3d_bf16", ()
         if stats and w.shape[0] in (128, 256, 512):
             import ctypes
-            slots = ctypes.c_int(0)
-            rc = lib.load().svr2_conv3d_stats_bf16(*args, None, 0, ctypes.byref(slots), lib.stream())   # size query
-            if rc:
-                raise lib.Svr2Error(f"svr2_conv3d_stats_bf16 query failed ({rc}): {lib.load().svr2_last_error().decode()}")
+            slots = ctypes.c_int(lib.load().svr2_conv_stat_slots(w.shape[0], Ho, Wo))
             part = torch.empty(T_out * slots.value * (w.shape[0] // 8) * 4, device=self.device, dtype=torch.float32)
             y.stats = (part, slots.value)
             name, extra = "svr2_conv3d_stats_bf16", (lib.ptr(part), part.numel() * 4, ctypes.byref(slots))
@@ -242,10 +330,7 @@ class B200VideoVAE(EngineModule):
         y = Act(h.T, h.H, h.W, Cout, out_pad, self.device)
         args = (lib.ptr(h.buf), h.pad + h.T, h.H, h.W, h.C, lib.ptr(w), Cout, kt, kh, kw, h.T, lib.ptr(b),
                 c_void_p(x.body_ptr()), C2, lib.ptr(y.buf), out_pad, int(out_pad > 0 and self._first))
-        slots = ctypes.c_int(0)
-        rc = lib.load().svr2_conv3d_shortcut_stats_bf16(*args, None, 0, ctypes.byref(slots), lib.stream())   # size query
-        if rc:
-            raise lib.Svr2Error(f"svr2_conv3d_shortcut_stats_bf16 query failed ({rc}): {lib.load().svr2_last_error().decode()}")
+        slots = ctypes.c_int(lib.load().svr2_conv_stat_slots(Cout, h.H, h.W))
         part = torch.empty(h.T * slots.value * (Cout // 8) * 4, device=self.device, dtype=torch.float32)
         y.stats = (part, slots.value)
         lib.call("svr2_conv3d_shortcut_stats_bf16", *args, lib.ptr(part), part.numel() * 4, ctypes.byref(slots), lib.stream(),
@@ -412,6 +497,11 @@ class B200VideoVAE(EngineModule):
         assert z.shape[0] == 1 and z.shape[1] == 16
         _, _, T, h, w = z.shape
         zin = z[0].to(self.device)
+        if self._use_native():
+            out = torch.empty(1, 3, 4 * T - 3, 8 * h, 8 * w, device=self.device, dtype=torch.bfloat16)
+            self._native_run(False, zin.contiguous(), T, h, w,
+                             None if self.split_size is None else max(1, self.split_size // 4), out)
+            return VAEOutput(sample=out.squeeze(2) if squeeze else out)
         if 4 * T - 3 <= self._frames_that_fit(8 * h, 8 * w):         # the whole clip fits: no slicing state needed
             size = T
         else:
@@ -466,6 +556,11 @@ class B200VideoVAE(EngineModule):
         assert x.shape[0] == 1 and x.shape[1] == 3
         _, _, T, H, Wd = x.shape
         xin = x[0].to(self.device)
+        if self._use_native() and H % 8 == 0 and Wd % 8 == 0:
+            out = torch.empty(1, 16, (T - 1) // 4 + 1, H // 8, Wd // 8, device=self.device, dtype=torch.bfloat16)
+            self._native_run(True, xin.contiguous(), T, H, Wd,
+                             None if self.split_size is None else max(4, self.split_size // 4 * 4), out)
+            return VAEOutput(latent=out.squeeze(2) if squeeze else out, latent_dist=None)
         if T <= self._frames_that_fit(H, Wd):
             size = max(4, (T + 3) // 4 * 4)
         else:                                                        # sample frames per slice, a multiple of 4

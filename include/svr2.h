@@ -60,7 +60,8 @@ int svr2_device_check(int* sm_count, int* cc_major, int* cc_minor);
  * NaDiT.forward (dit_3b/nadit.py:190-248, dit_7b/nadit.py:152-190) for b = 1 at the folded timestep. */
 typedef struct svr2_engine svr2_t;
 typedef struct svr2_model_desc {
-  int variant;        /* 0 = SeedVR2-3B structure, 1 = 7B structure (RoPE kind, window-size tables) */
+  int variant;        /* 0 = SeedVR2-3B structure, 1 = 7B structure (RoPE kind, window-size tables); 2 = the video VAE
+                       * (s8_c16_t4 causal 3-D conv autoencoder; the remaining fields are ignored) */
   int dim, heads;     /* dim == heads * 128 */
   int layers, mm_layers;
   int txt_in_dim, in_ch, out_ch;
@@ -96,6 +97,30 @@ int svr2_dit_forward(svr2_t* engine, const void* vid, const void* txt, int T, in
 int svr2_dit_forward_ws(svr2_t* engine, const void* vid, const void* txt, int T, int H, int W, int txt_len, void* out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Video VAE on a handle created with svr2_model_desc.variant == 2 (native host runtime csrc/vae_engine.cu).
+ * Replaces VideoAutoencoderKLWrapper.encode / .decode (video_vae_v3/modules/attn_video_vae.py:1680-1698) incl. the
+ * temporal slicing with the causal convs' memories (slicing_encode / slicing_decode :1254-1300,
+ * causal_inflation_lib.py:306-352).  Weights (svr2_load_weights) carry the checkpoint's key names in the kernels'
+ * layout: conv weights [Cout, kt, kh, kw, Cin] bf16 (rank 5, channels padded to a multiple of 64), "<resnet>.conv2+shortcut.
+ * weight / .bias" = [W2 ; Wsc] rows and summed biases for resnets with a channel change, "upscale_conv.weight" [r*C, C],
+ * "encoder.conv_in.weight" [128, 128] (im2col, K = 81 padded), "decoder.conv_out.weight" [81, 128] (tap-major), vectors bf16.
+ *
+ * All activations live in ONE workspace: svr2_vae_workspace_bytes() is exact (a dry run of the same sequence over a
+ * first-fit arena), for direction 0 = encode (T sample frames of H x W pixels, H and W multiples of 8) or 1 = decode
+ * (T latent frames of H x W latent pixels) cut into temporal slices of `slice_frames` (encode: sample frames, a multiple
+ * of 4; decode: latent frames; 0 = un-sliced; the first slice additionally holds frame 0, like the reference's).  The
+ * sliced result is bit-identical to the un-sliced one.  workspace == NULL: the engine owns (and grows) the workspace.
+ *   encode: x [3, T, H, W] (x_dtype 0 f32 | 1 bf16 | 2 f16, values in [-1, 1]) -> latent [16, (T-1)/4+1, H/8, W/8] bf16
+ *           (posterior mode; multiply by the scaling factor outside);
+ *   decode: z [16, T, h, w] -> sample [3, 4T-3, 8h, 8w] bf16. */
+size_t svr2_vae_workspace_bytes(svr2_t* engine, int direction, int T, int H, int W, int slice_frames);
+int svr2_vae_encode(svr2_t* engine, const void* x, int x_dtype, int T, int H, int W, int slice_frames, void* latent,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int svr2_vae_decode(svr2_t* engine, const void* z, int z_dtype, int T, int h, int w, int slice_frames, void* sample,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* kernels launched by the handle's last svr2_vae_encode / svr2_vae_decode */
+int64_t svr2_vae_last_launches(svr2_t* engine);
+
 /* ---- K1: Linear.  out[M,N] = epi(a[M,K] @ w[N,K]^T).  Replaces nn.Linear at
  * dit_3b/nablocks/attention/mmattn.py:56-59,173,269; dit_3b/mlp.py:56-61; dit_7b/mlp.py:35-43;
  * dit_3b/patch/patch_v1.py:37,62; dit_3b/embedding.py:38-40; diffusers Attention to_q/k/v/out
@@ -119,6 +144,10 @@ int svr2_conv3d_stats_bf16(const void* x, int T_in_total, int H, int W, int Cin,
                            int kw, int stride_t, int stride_hw, int pad_hw, int T_out, int epi_flags, const void* bias,
                            const void* residual, void* y, int out_t_pad, int out_dup_head, int ldc, void* stat_partial,
                            int64_t stat_bytes, int* stat_slots, void* stream);
+
+/* slots per frame of the statistics output for an output of H_out x W_out pixels (pure function of the tile shape:
+ * lets a caller plan memory without the NULL query) */
+int svr2_conv_stat_slots(int Cout, int H_out, int W_out);
 
 /* Stride-1 causal conv with the ResnetBlock3D 1x1x1 conv_shortcut fused in as extra K-blocks (attn_video_vae.py:311-362:
  * `x = conv_shortcut(x); return x + hidden`): y = conv(x; w[:, :kt*kh*kw*Cin]) + x2 . w[:, kt*kh*kw*Cin:]^T + bias,

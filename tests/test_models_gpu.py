@@ -302,6 +302,51 @@ def test_dit_native_runtime_equals_python_sequencing(pkg, name):
     assert torch.equal(out_n, dit.B200NaDiT(cfg, sd)(vid.cuda(), txt.cuda(), [[T, H, W]], [[l]]).vid_sample)
 
 
+@pytest.mark.parametrize("split", [None, 4, 8])
+def test_vae_native_runtime_equals_python_sequencing(vae_pair, split):
+    """svr2_vae_encode / svr2_vae_decode (C++ host runtime on a svr2_t handle: kernel sequence, temporal slices with the
+    conv memories, one first-fit activation arena) against the same clip sequenced by the Python module with torch
+    allocations: same kernels, same order -> bit-identical results, un-sliced and sliced; the handle's workspace query is
+    exact (one aligned block less is refused) and an engine-owned workspace gives the same result."""
+    lib = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.lib")
+    eng, _ = vae_pair
+    g = torch.Generator().manual_seed(21)
+    z = torch.randn(1, 16, 5, 18, 24, generator=g).cuda()                  # n = 432 keys: single-pass attention path
+    x = (torch.rand(1, 3, 17, 144, 192, generator=g) * 2 - 1).cuda()
+    eng.set_causal_slicing(split_size=split)
+    try:
+        eng.native = False
+        dec_p, enc_p = eng.decode(z).sample.clone(), eng.encode(x).latent.clone()
+        eng.native = True
+        n0 = lib.LAUNCHES
+        dec_n = eng.decode(z).sample.clone()
+        launches = lib.LAUNCHES - n0
+        enc_n = eng.encode(x).latent.clone()
+    finally:
+        eng.native = True
+        eng.set_causal_slicing(split_size=None)
+    assert launches > 300
+    assert dec_n.shape == dec_p.shape == (1, 3, 17, 144, 192) and enc_n.shape == enc_p.shape == (1, 16, 5, 18, 24)
+    assert torch.equal(dec_n, dec_p), f"decode (split {split}): native vs python {psnr(dec_n, dec_p):.1f} dB"
+    assert torch.equal(enc_n, enc_p), f"encode (split {split}): native vs python {psnr(enc_n, enc_p):.1f} dB"
+    # fp16 input, engine-owned workspace, explicit too-small workspace
+    h = eng.native_handle()
+    sl = 0 if split is None else max(1, split // 4)
+    need = eng.workspace_bytes(False, 5, 18, 24, sl)
+    out = torch.empty_like(dec_n)
+    zh = z[0].half().contiguous()
+    ref = eng.decode(zh[None]).sample
+    L = lib.load()
+    assert L.svr2_vae_decode(h, lib.ptr(zh), 2, 5, 18, 24, sl, lib.ptr(out), None, 0, lib.stream()) == 0
+    assert torch.equal(out, ref)
+    ws = torch.empty(need, device="cuda", dtype=torch.uint8)
+    assert L.svr2_vae_decode(h, lib.ptr(zh), 2, 5, 18, 24, sl, lib.ptr(out), lib.ptr(ws), need - 256, lib.stream()) != 0
+    assert b"workspace" in L.svr2_engine_last_error(h)
+    out.zero_()
+    assert L.svr2_vae_decode(h, lib.ptr(zh), 2, 5, 18, 24, sl, lib.ptr(out), lib.ptr(ws), need, lib.stream()) == 0
+    assert torch.equal(out, ref)
+
+
 def test_vae_attention_single_pass_equals_two_pass_and_falls_back(vae_pair):
     """Mid-block attention (attn_video_vae.py:656-668): the single-pass path (sampled reference exponent, un-normalised
     probabilities, row-sum division in the P V epilogue) against the exact two-pass path on the same input, and the
