@@ -355,7 +355,7 @@ class B200NaDiT(EngineModule):
 
     # ---- forward -----------------------------------------------------------
     @torch.no_grad()
-    def forward(self, vid, txt, vid_shape, txt_shape, timestep=None, disable_cache=False):
+    def forward(self, vid, txt, vid_shape, txt_shape, timestep=None, disable_cache=False, workspace=None):
         """vid (T*H*W, 33), txt (l, 5120); vid_shape [[T,H,W]], txt_shape [[l]] (b = 1)."""
         self._require_cuda("B200NaDiT.forward")
         if timestep is not None:
@@ -380,7 +380,10 @@ class B200NaDiT(EngineModule):
             out = torch.empty(T * H * Wd, cfg["out_ch"], device=dev, dtype=torch.bfloat16)
             # the workspace comes from torch's caching allocator (and from the capture pool inside a CUDA graph) and goes
             # back to it after the forward: the VAE phases need those bytes (35 GB at a 65-frame 4K clip)
-            ws = torch.empty(self.workspace_bytes(T, H, Wd, l), device=dev, dtype=torch.uint8)
+            # (or is the clip's shared workspace, pipeline.SeedVR2Engine.clip_to_sample)
+            need = self.workspace_bytes(T, H, Wd, l)
+            ws = workspace if (workspace is not None and workspace.numel() >= need) else \
+                torch.empty(need, device=dev, dtype=torch.uint8)
             lib.call("svr2_dit_forward_ws", self.native_handle(), lib.ptr(vid), lib.ptr(txt), T, H, Wd, l, lib.ptr(out),
                      lib.ptr(ws), ws.numel(), lib.stream())
             n_l = cfg["layers"]

@@ -59,29 +59,45 @@ class SeedVR2Engine:
 
     # ---- VideoDiffusionInfer.vae_encode ---------------------------------
     @torch.no_grad()
-    def vae_encode(self, clip: torch.Tensor) -> torch.Tensor:
+    def vae_encode(self, clip: torch.Tensor, workspace=None) -> torch.Tensor:
         """clip (3,T,H,W) in [-1,1] -> latent (T',h,w,16) bf16, scaled."""
-        z = self.vae.encode(clip[None].to(self.device, torch.bfloat16)).latent   # (1,16,T',h,w)
+        z = self.vae.encode(clip[None].to(self.device, torch.bfloat16), workspace=workspace).latent   # (1,16,T',h,w)
         z = (z - SHIFTING_FACTOR) * SCALING_FACTOR
         return z[0].permute(1, 2, 3, 0).contiguous()
 
     # ---- VideoDiffusionInfer.inference ------------------------------------
     @torch.no_grad()
-    def inference(self, noise: torch.Tensor, latent: torch.Tensor) -> torch.Tensor:
+    def inference(self, noise: torch.Tensor, latent: torch.Tensor, workspace=None) -> torch.Tensor:
         """noise, latent (T',h,w,16) -> x0 (T',h,w,16).  condition = cat[latent, 1] (task 'sr')."""
         T, h, w, c = latent.shape
         ones = torch.ones(T, h, w, 1, device=self.device, dtype=torch.bfloat16)
         vid = torch.cat([noise.to(self.device, torch.bfloat16), latent.to(torch.bfloat16), ones], -1)
-        v = self.dit(vid.view(T * h * w, 2 * c + 1), self.txt, [[T, h, w]], [[self.txt.shape[0]]]).vid_sample
+        v = self.dit(vid.view(T * h * w, 2 * c + 1), self.txt, [[T, h, w]], [[self.txt.shape[0]]],
+                     workspace=workspace).vid_sample
         return noise.to(self.device, torch.bfloat16) - v.view(T, h, w, c)
 
     # ---- VideoDiffusionInfer.vae_decode -----------------------------------
     @torch.no_grad()
-    def vae_decode(self, latent: torch.Tensor) -> torch.Tensor:
+    def vae_decode(self, latent: torch.Tensor, workspace=None) -> torch.Tensor:
         """latent (T',h,w,16) -> sample (3,T,H,W) bf16 in ~[-1,1]."""
         z = latent.permute(3, 0, 1, 2)[None]
         z = z / SCALING_FACTOR + SHIFTING_FACTOR
-        return self.vae.decode(z).sample[0]
+        return self.vae.decode(z, workspace=workspace).sample[0]
+
+    def clip_workspace(self, T: int, Hp: int, Wp: int) -> Optional[torch.Tensor]:
+        """ONE workspace for the three phases of a clip of T (4n+1) frames at Hp x Wp (multiples of 16): the maximum of
+        the exact needs of VAE encode, the DiT forward and VAE decode (svr2_vae_workspace_bytes / svr2_workspace_bytes),
+        with the VAE passes temporally sliced until they fit the free HBM.  The phases run one after the other on one
+        stream, so they can share the bytes; the block comes from torch's caching allocator (the capture pool inside a
+        CUDA graph) and goes back to it after the clip.  None when a phase runs on the Python sequencing (profiling)."""
+        from . import lib
+        if not (self.vae._use_native() and self.dit.native and lib.PROFILER is None):
+            return None
+        Tl, h, w = (T - 1) // 4 + 1, Hp // 8, Wp // 8
+        budget = int(0.92 * self.vae._free_bytes()) - 2 * 3 * T * Hp * Wp * 2      # the decoded clip and its crop
+        need = max(self.vae.plan_slices(True, T, Hp, Wp, budget)[1], self.vae.plan_slices(False, Tl, h, w, budget)[1],
+                   self.dit.workspace_bytes(Tl, h, w, self.txt.shape[0]))
+        return torch.empty(need, device=self.device, dtype=torch.uint8)
 
     def latent_shape(self, frames: torch.Tensor, resolution: Optional[int] = None, max_resolution: int = 0):
         """(T', h, w, 16) of the latent ``upscale_clip`` will produce for ``frames`` (T,h,w,3)."""
@@ -123,12 +139,15 @@ class SeedVR2Engine:
         tf = preprocess.VideoTransform(res, max_resolution)
         H0, W0 = tf.true_size(frames.shape[1], frames.shape[2])
         x = tf.run(x, channels_last=True)                           # (3, T, Hp, Wp) bf16 in [-1,1]
-        latent = self.vae_encode(x)
+        ws = self.clip_workspace(x.shape[1], x.shape[2], x.shape[3])
+        kw = {} if ws is None else {"workspace": ws}
+        latent = self.vae_encode(x, **kw)
         if noise is None:
             g = torch.Generator(device=self.device).manual_seed(seed)
             noise = torch.randn(latent.shape, generator=g, device=self.device, dtype=torch.bfloat16)
-        x0 = self.inference(noise, latent)
-        y = self.vae_decode(x0)                                     # (3,T,H,W)
+        x0 = self.inference(noise, latent, **kw)
+        y = self.vae_decode(x0, **kw)                               # (3,T,H,W)
+        del ws, kw
         sample = y[:, :T0, :H0, :W0].permute(1, 0, 2, 3)            # t c h w, the layout of phase 4
         style = x[:, :T0, :H0, :W0].permute(1, 0, 2, 3)            # the transformed input clip in [-1,1]
         return sample, style

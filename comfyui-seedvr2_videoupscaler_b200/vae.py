@@ -141,24 +141,37 @@ class B200VideoVAE(EngineModule):
         free, _ = torch.cuda.mem_get_info(self.device)
         return free + torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
 
-    def _native_run(self, encode: bool, src: torch.Tensor, T: int, H: int, W: int, cap, out: torch.Tensor):
-        """Temporal slice length: the largest (un-sliced first, then ``cap`` = set_causal_slicing's split, then halving)
-        whose EXACT workspace fits the free HBM.  The workspace comes from torch's caching allocator (the capture pool
-        inside a CUDA graph) and returns to it after the call."""
+    def plan_slices(self, encode: bool, T: int, H: int, W: int, budget: Optional[int] = None):
+        """(slice_frames, workspace bytes) of a native encode (T sample frames of H x W) / decode (T latent frames of
+        H x W latent pixels): the longest temporal slice — un-sliced first, then set_causal_slicing's split, then shorter
+        ones — whose EXACT workspace fits ``budget`` bytes (default: 92 % of the free HBM incl. torch's cached blocks)."""
         step = 4 if encode else 1
+        cap = None if self.split_size is None else (max(4, self.split_size // 4 * 4) if encode else max(1, self.split_size // 4))
         can_slice = not (encode and (T - 1) % 4)       # only 4n+1-frame clips continue the temporal stride phase
-        sz = 0 if (cap is None or T - 1 <= cap or not can_slice) else max(step, cap // step * step)
+        sz = 0 if (cap is None or T - 1 <= cap or not can_slice) else cap
         need = self.workspace_bytes(encode, T, H, W, sz)
-        if can_slice and not torch.cuda.is_current_stream_capturing():
-            budget = int(0.92 * self._free_bytes())
-            while need > budget:
-                cur = sz if sz else T - 1
-                nxt = max(step, (cur // 2) // step * step)
-                if nxt >= cur:
+        if can_slice:
+            if budget is None:
+                budget = int(0.92 * self._free_bytes())
+            while need > budget:                       # each candidate is one dry run of the C++ sequence (no launches)
+                cur = sz if sz else (T - 1 + step - 1) // step * step
+                if cur <= step:
                     break
-                sz = nxt
+                sz = cur - step
                 need = self.workspace_bytes(encode, T, H, W, sz)
-        ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        return sz, need
+
+    def _native_run(self, encode: bool, src: torch.Tensor, T: int, H: int, W: int, out: torch.Tensor, workspace=None):
+        """``workspace``: a uint8 CUDA tensor shared by the phases of a clip (pipeline.ClipWorkspace) or None — then it
+        comes from torch's caching allocator (the capture pool inside a CUDA graph) and returns to it after the call."""
+        if workspace is not None:
+            sz, need = self.plan_slices(encode, T, H, W, budget=workspace.numel())
+            if need > workspace.numel():
+                raise lib.Svr2Error(f"B200VideoVAE: workspace of {workspace.numel()} bytes given, {need} needed")
+            ws = workspace
+        else:
+            sz, need = self.plan_slices(encode, T, H, W)
+            ws = torch.empty(need, device=self.device, dtype=torch.uint8)
         dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[src.dtype]
         lib.call("svr2_vae_encode" if encode else "svr2_vae_decode", self.native_handle(), lib.ptr(src), dt, T, H, W, sz,
                  lib.ptr(out), lib.ptr(ws), ws.numel(), lib.stream())
@@ -485,7 +498,7 @@ class B200VideoVAE(EngineModule):
 
     # ---- public API --------------------------------------------------------
     @torch.no_grad()
-    def decode(self, z: torch.Tensor, return_dict=True, tiled=False, tile_size=None, tile_overlap=None):
+    def decode(self, z: torch.Tensor, return_dict=True, tiled=False, tile_size=None, tile_overlap=None, workspace=None):
         """z (1,16,T,h,w) or (1,16,h,w) -> .sample (1,3,4T-3,8h,8w) bf16 (Decoder3D.forward)."""
         self._require_cuda("B200VideoVAE.decode")
         squeeze = z.ndim == 4
@@ -499,8 +512,7 @@ class B200VideoVAE(EngineModule):
         zin = z[0].to(self.device)
         if self._use_native():
             out = torch.empty(1, 3, 4 * T - 3, 8 * h, 8 * w, device=self.device, dtype=torch.bfloat16)
-            self._native_run(False, zin.contiguous(), T, h, w,
-                             None if self.split_size is None else max(1, self.split_size // 4), out)
+            self._native_run(False, zin.contiguous(), T, h, w, out, workspace)
             return VAEOutput(sample=out.squeeze(2) if squeeze else out)
         if 4 * T - 3 <= self._frames_that_fit(8 * h, 8 * w):         # the whole clip fits: no slicing state needed
             size = T
@@ -543,7 +555,7 @@ class B200VideoVAE(EngineModule):
         return out
 
     @torch.no_grad()
-    def encode(self, x: torch.Tensor, return_dict=True, tiled=False, tile_size=None, tile_overlap=None):
+    def encode(self, x: torch.Tensor, return_dict=True, tiled=False, tile_size=None, tile_overlap=None, workspace=None):
         """x (1,3,T,H,W) or (1,3,H,W) in [-1,1] -> .latent (1,16,(T-1)/4+1,H/8,W/8) bf16 = posterior mode
         (Encoder3D.forward + DiagonalGaussianDistribution.mode, attn_video_vae.py:1680-1689)."""
         self._require_cuda("B200VideoVAE.encode")
@@ -558,8 +570,7 @@ class B200VideoVAE(EngineModule):
         xin = x[0].to(self.device)
         if self._use_native() and H % 8 == 0 and Wd % 8 == 0:
             out = torch.empty(1, 16, (T - 1) // 4 + 1, H // 8, Wd // 8, device=self.device, dtype=torch.bfloat16)
-            self._native_run(True, xin.contiguous(), T, H, Wd,
-                             None if self.split_size is None else max(4, self.split_size // 4 * 4), out)
+            self._native_run(True, xin.contiguous(), T, H, Wd, out, workspace)
             return VAEOutput(latent=out.squeeze(2) if squeeze else out, latent_dist=None)
         if T <= self._frames_that_fit(H, Wd):
             size = max(4, (T + 3) // 4 * 4)

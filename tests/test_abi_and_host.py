@@ -293,6 +293,7 @@ def test_clip_runner_control_flow_with_stubbed_kernels(pkg, monkeypatch):
     monkeypatch.setattr(preprocess.VideoTransform, "run", fake_run)
     eng.vae_encode = lambda x: torch.zeros((x.shape[1] - 1) // 4 + 1, x.shape[2] // 8, x.shape[3] // 8, 16, dtype=torch.bfloat16)
     eng.inference = lambda noise, latent: noise
+    eng.clip_workspace = lambda T, Hp, Wp: None                             # no native runtime on the CPU
     eng.vae_decode = lambda z: torch.ones(3, 4 * z.shape[0] - 3, 8 * z.shape[1], 8 * z.shape[2], dtype=torch.bfloat16) * 0.5
     monkeypatch.setattr(color_fix, "apply_color_correction", lambda s_, st, mode, debug=None: (s_.float() * 0 + st.float()).to(torch.bfloat16))
     monkeypatch.setattr(color_fix, "sample_to_image", lambda s_: (s_.float().permute(0, 2, 3, 1).clamp(-1, 1) * 0.5 + 0.5).to(torch.bfloat16))
