@@ -299,7 +299,7 @@ def main():
     peak_mem_native = torch.cuda.max_memory_allocated()
     # ---- region P: the same steps with per-kernel CUDA events on the launching stream (per-call events need the Python
     # sequencing of the same kernels): the roofline and the per-kernel table come from here, not the headline value
-    prof_steps = min(args.steps, 3)
+    prof_steps = 1 if ms / args.steps > 5000 else min(args.steps, 3)      # long clips: one profiled pass is enough
     step(frames_dev)            # the Python sequencing allocates per activation: first pass fills the allocator's cache
     lib.PROFILER = lib.Profiler()
     lib.PROFILER.detail = args.detail

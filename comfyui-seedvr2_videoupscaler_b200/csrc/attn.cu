@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 #include "svr2_internal.h"
@@ -68,6 +69,10 @@ struct AttnParams {
 // Inside an item the software pipeline is the same as before: S_{j+1} = Q K_{j+1}^T is issued as soon as the softmax
 // warps have pulled S_j into registers, P_j V_j runs while tile j+1 is in its softmax; K is double-buffered, V single.
 // All barrier phases are tracked with running counters (tiles / items processed by this CTA).
+// POLY: three of every eight column pairs of a full tile take their exp2 on the FMA pipe (ptx.cuh exp2_poly, relative
+// error 5e-5 against the 4e-3 of the bf16 rounding that follows): the 64 ex2 per row and tile keep the MUFU pipe busy
+// exactly as long as the tile's two MMAs keep the tensor pipe (512 cycles each), and both of an SM's CTAs share it.
+template <bool POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -250,7 +255,8 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc_fence_before();
         mbar_arrive(s_free);                      // S may be overwritten by the next QK^T
         const int kv_valid = len - j * ATT_BN;    // columns >= kv_valid are padding / the next sequence
-        if (kv_valid < ATT_BN) {                  // only the last tile of a sequence is ragged
+        const bool ragged = kv_valid < ATT_BN;
+        if (ragged) {                             // only the last tile of a sequence is ragged
 #pragma unroll
           for (int c = 0; c < ATT_BN; ++c)
             if (c >= kv_valid) sv[c] = 0xff800000u;   // -inf
@@ -274,12 +280,24 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         // P = exp2(s * sc - m_new * sc): packed fp32x2 FMAs, four independent partial sums
         float2 ls[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         uint32_t pk[ATT_BN / 2];
+        if (POLY && !ragged) {                    // (a masked -inf would come out of the polynomial as 2^-125, not 0)
 #pragma unroll
-        for (int c = 0; c < ATT_BN; c += 2) {
-          const float2 t = ffma2(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sc2, nmb);
-          const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
-          ls[(c >> 1) & 1] = fadd2(ls[(c >> 1) & 1], e);
-          pk[c / 2] = pack_bf16x2(e.x, e.y);
+          for (int c = 0; c < ATT_BN; c += 2) {
+            const float2 t = ffma2(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sc2, nmb);
+            const int i8 = (c >> 1) & 7;
+            const bool poly = i8 == 1 || i8 == 4 || i8 == 6;          // folds after unrolling
+            const float2 e = poly ? make_float2(exp2_poly(t.x), exp2_poly(t.y)) : make_float2(fast_exp2(t.x), fast_exp2(t.y));
+            ls[(c >> 1) & 1] = fadd2(ls[(c >> 1) & 1], e);
+            pk[c / 2] = pack_bf16x2(e.x, e.y);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < ATT_BN; c += 2) {
+            const float2 t = ffma2(make_float2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1])), sc2, nmb);
+            const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));
+            ls[(c >> 1) & 1] = fadd2(ls[(c >> 1) & 1], e);
+            pk[c / 2] = pack_bf16x2(e.x, e.y);
+          }
         }
         const float lsum = (ls[0].x + ls[1].x) + (ls[0].y + ls[1].y);
         if (j > 0) {
@@ -360,10 +378,16 @@ extern "C" int svr2_attn_varlen_bf16(const void* q, const void* k, const void* v
   if (n_seq <= 0 || total <= 0) return SVR2_OK;
   if (max_seqlen <= 0) return set_error(SVR2_ERR_ARG, "svr2_attn_varlen_bf16: max_seqlen must be > 0");
   static bool configured[64] = {};                // the attribute is per (function, device)
+  static int poly = -1;                           // SVR2_ATTN_POLY=1: part of the exp2 on the FMA pipe (A/B switch)
+  if (poly < 0) {
+    const char* e = getenv("SVR2_ATTN_POLY");
+    poly = e ? atoi(e) : 0;
+  }
   const int dev = current_device();
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         AttnSmem::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(attn_varlen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_varlen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
     configured[dev] = true;
   }
@@ -388,6 +412,7 @@ extern "C" int svr2_attn_varlen_bf16(const void* q, const void* k, const void* v
   if (n_work > 0x7fffffffLL) return set_error(SVR2_ERR_ARG, "svr2_attn_varlen_bf16: too many work items");
   p.n_work = (int)n_work;
   const int grid = (int)(n_work < 2LL * num_sms() ? n_work : 2LL * num_sms());   // persistent: two CTAs per SM
-  attn_varlen_kernel<<<grid, ATT_THREADS, AttnSmem::kTotal, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  if (poly) attn_varlen_kernel<true><<<grid, ATT_THREADS, AttnSmem::kTotal, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  else attn_varlen_kernel<false><<<grid, ATT_THREADS, AttnSmem::kTotal, (cudaStream_t)stream>>>(tq, tk, tv, p);
   return check_launch("attn_varlen");
 }

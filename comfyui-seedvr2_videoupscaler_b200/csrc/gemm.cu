@@ -1055,6 +1055,249 @@ int num_sms() {
   return g_num_sms[dev];
 }
 
+// ======================================================================================================================
+// W-reuse conv kernel (Cout <= 128, stride 1, 3x3 spatial taps; swap-AB: M = 128 output channels, N = 256 output pixels).
+//
+// The generic swap-AB kernel moves 48 KB of operands L2 -> SM per 128x256x64 k-block (16 KB of weights + a 32 KB
+// activation box per tap): 96 B/clk and SM, ~13 TB/s chip-wide at 1.2 PFLOP/s — the L2 slices' throughput ceiling, which
+// is what holds those layers at 87 % tensor-pipe activity.  Here a tile is ONE output row segment of 256 pixels, so the
+// three horizontal taps of a (kt, kh, 64-channel block) read the SAME 258-pixel input row segment: it is loaded once
+// (two TMA boxes: 256 + 8 pixels, 128B-swizzled rows) and the three MMAs of the kw taps address it through UMMA
+// descriptors whose start address is shifted by kw rows of 128 B.  Activation traffic drops 3x (27 KB instead of 48 KB
+// per k-block).  Two rings: NB activation stages (33 KB, three k-blocks each) fed by warp 0, NA weight stages (16 KB,
+// one k-block each) fed by warp 3; warp 1 issues, warp 2 owns TMEM, warps 4-11 run the swap-AB epilogue (bias,
+// residual, halo duplication, GroupNorm partial sums) of the generic kernel.
+struct WrSmem {
+  static constexpr int kNB = 3, kNA = 5;
+  static constexpr int kBRows = 264;                       // 256 + 2 halo pixels, rounded to whole 8-row swizzle atoms
+  static constexpr int kBBytes = kBRows * 128;             // 33 792
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;    // 16 384
+  static constexpr int kAOffset = kNB * kBBytes;
+  static constexpr int kStagingOffset = kAOffset + kNA * kABytes;
+  static constexpr int kStagingBytes = 8 * 4096;
+  static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+};
+static_assert(WrSmem::kTotal <= 232448, "W-reuse conv: shared memory budget");
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_wreuse_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x_tail,
+                   const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x2,
+                   const GemmParams p, const int bo_mode) {
+  using L = WrSmem;
+  constexpr int ACC_STRIDE = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* b_empty = b_full + L::kNB;
+  uint64_t* a_full = b_empty + L::kNB;
+  uint64_t* a_empty = a_full + L::kNA;
+  uint64_t* tmem_full = a_empty + L::kNA;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_x_tail);
+    tma_prefetch_desc(&tmap_w);
+    if (p.extra_blocks) tma_prefetch_desc(&tmap_x2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < L::kNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < L::kNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = p.num_m_tiles;                 // one n-tile: Cout <= 128
+  const int taps_t = p.taps_t, cin_blocks = p.cin_blocks, extra = p.extra_blocks;
+  const int n_groups = taps_t * 3 * cin_blocks;        // (kt, kh, cb) activation stages of three k-blocks each
+
+  if (warp == 0) {
+    // ------------------------- activation rows: one stage per (kt, kh, cb) + one per shortcut block
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int t_o, th, tw;
+        conv_tile(p, tile, t_o, th, tw);
+        const int w0 = tw * 256;
+        for (int kt_ = 0; kt_ < taps_t; ++kt_) {
+          const int t_in = t_o * p.stride_t + kt_;
+          for (int kh_ = 0; kh_ < 3; ++kh_) {
+            const int h_in = th + kh_ - 1;
+            for (int cb = 0; cb < cin_blocks; ++cb) {
+              mbar_wait(&b_empty[stage], phase ^ 1);
+              uint8_t* sb = smem + stage * L::kBBytes;
+              mbar_expect_tx(&b_full[stage], L::kBBytes);
+              tma_load_4d(sb, &tmap_x, &b_full[stage], cb * BLOCK_K, w0 - 1, h_in, t_in);
+              tma_load_4d(sb + 256 * 128, &tmap_x_tail, &b_full[stage], cb * BLOCK_K, w0 + 255, h_in, t_in);
+              if (++stage == L::kNB) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+        for (int cb = 0; cb < extra; ++cb) {            // fused 1x1x1 shortcut: the block input at the output pixels
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          mbar_expect_tx(&b_full[stage], 256 * 128);
+          tma_load_4d(smem + stage * L::kBBytes, &tmap_x2, &b_full[stage], cb * BLOCK_K, w0, th, t_o);
+          if (++stage == L::kNB) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------- weight k-blocks, in the order the MMA warp consumes them
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int cin = p.cin;
+      auto load = [&](int kcol) {
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        mbar_expect_tx(&a_full[stage], L::kABytes);
+        tma_load_2d(smem + L::kAOffset + stage * L::kABytes, &tmap_w, &a_full[stage], kcol, 0);
+        if (++stage == L::kNA) { stage = 0; phase ^= 1; }
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int g = 0; g < taps_t * 3; ++g)            // g = kt * 3 + kh
+          for (int cb = 0; cb < cin_blocks; ++cb)
+            for (int kw_ = 0; kw_ < 3; ++kw_) load((g * 3 + kw_) * cin + cb * BLOCK_K);
+        for (int cb = 0; cb < extra; ++cb) load(taps_t * 9 * cin + cb * BLOCK_K);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, 256);
+      int bs = 0, as = 0, acc = 0;
+      uint32_t bph = 0, aph = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        uint32_t first = 1;
+        for (int g = 0; g < n_groups + extra; ++g) {
+          const int n_taps = g < n_groups ? 3 : 1;
+          mbar_wait(&b_full[bs], bph);
+          const uint32_t b_addr = smem_u32(smem + bs * L::kBBytes);
+          for (int kw_ = 0; kw_ < n_taps; ++kw_) {
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem + L::kAOffset + as * L::kABytes));
+            // the tap's 256 operand rows start kw rows (of 128 B) into the stage; base offset = the start row's phase
+            // inside the 8-row swizzle atom
+            uint64_t b_desc = umma_desc_kmajor_sw128(b_addr + kw_ * 128);
+            if (bo_mode) b_desc |= static_cast<uint64_t>(kw_) << 49;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, first ? 0u : 1u);
+              first = 0;
+            }
+            umma_commit(&a_empty[as]);
+            if (++as == L::kNA) { as = 0; aph ^= 1; }
+          }
+          umma_commit(&b_empty[bs]);
+          if (++bs == L::kNB) { bs = 0; bph ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------- epilogue: the generic kernel's swap-AB epilogue (lanes = channels, columns = pixels)
+    const int q = warp & 3, half = (warp - 4) >> 2, row = q * 32 + lane;
+    uint8_t* slab = smem + L::kStagingOffset + (warp - 4) * 4096;
+    const int epi = p.epi;
+    const __nv_bfloat16* __restrict__ bias = p.bias;
+    const __nv_bfloat16* __restrict__ resid = p.residual;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int t_o, th, tw;
+      conv_tile(p, tile, t_o, th, tw);
+      const int r = th * p.tiles_w + tw;
+      const int w0 = tw * 256;
+      const float bsc = ((epi & EPI_BIAS) && row < p.N) ? __bfloat162float(bias[row]) : 0.f;
+      const long long fbase = (long long)(t_o + p.out_t_pad) * p.out_frame_stride + q * 32;
+      const bool dup_t = p.out_dup_head && t_o == 0;
+      mbar_wait_backoff(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_STRIDE;
+      unsigned short* slab16 = reinterpret_cast<unsigned short*>(slab);
+      float4 st = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= half * 128 + 128) {
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          slab16[j * 64 + lane] = (unsigned short)(__float_as_uint(bf16_rne(__uint_as_float(v[j]) + bsc)) >> 16);
+        __syncwarp();
+        const int chn = lane & 3, psub = lane >> 2;
+        long long off[4];
+        int flags[4];
+        uint4 rv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int w = w0 + c0 + i * 8 + psub;
+          const bool ok = (w < p.W_out) && (q * 32 + chn * 8 < p.N);
+          off[i] = fbase + ((long long)th * p.W_out + w) * p.ldc + chn * 8;
+          flags[i] = ok ? (dup_t ? 3 : 1) : 0;
+          if ((epi & EPI_RESIDUAL) && ok) rv[i] = *reinterpret_cast<const uint4*>(resid + off[i]);
+        }
+        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (!(flags[i] & 1)) continue;
+          uint4 d = *reinterpret_cast<const uint4*>(slab + (i * 8 + psub) * 128 + chn * 16);
+          if (epi & EPI_RESIDUAL) {
+            const uint32_t dw[4] = {d.x, d.y, d.z, d.w}, rw[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = pack_bf16x2(__uint_as_float(dw[e] << 16) + __uint_as_float(rw[e] << 16),
+                                 __uint_as_float(dw[e] & 0xffff0000u) + __uint_as_float(rw[e] & 0xffff0000u));
+            d = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          *reinterpret_cast<uint4*>(ob + off[i]) = d;
+          if (p.stat_partial) stat_acc(st, d);
+          if (flags[i] & 2) {
+            *reinterpret_cast<uint4*>(ob + off[i] - p.out_frame_stride) = d;
+            *reinterpret_cast<uint4*>(ob + off[i] - 2 * p.out_frame_stride) = d;
+          }
+        }
+        __syncwarp();
+      }
+      if (p.stat_partial) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          st.x += __shfl_xor_sync(0xffffffffu, st.x, o); st.y += __shfl_xor_sync(0xffffffffu, st.y, o);
+          st.z += __shfl_xor_sync(0xffffffffu, st.z, o); st.w += __shfl_xor_sync(0xffffffffu, st.w, o);
+        }
+        if (lane < 4 && t_o < p.T_out) {
+          const int octet = (q * 32) / 8 + lane;
+          if (octet * 8 < p.N) p.stat_partial[((long long)t_o * p.stat_slots + r * 2 + half) * (p.N / 8) + octet] = st;
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false, int EPI_CT = -1>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, cudaStream_t stream,
                        const CUtensorMap* ta2_opt = nullptr) {
@@ -1381,6 +1624,22 @@ extern "C" int svr2_conv3d_shortcut_stats_bf16(const void* x, int T_in_total, in
 
 // Output tile of the implicit-GEMM conv.  Cout <= 128: swap operands (128 channels x 256 pixels per tile); else
 // 128 pixels x up to 256 channels.  bw x bh output pixels (128, or 256 when swapped).
+// W-reuse conv (conv_wreuse_kernel): activation maps with 256- and 8-pixel row boxes; the weight map (box 64 x 128 rows) and
+// the shortcut tensor's map (box 64 x 256 pixels) are the generic kernel's.
+static int launch_conv_wreuse(const void* x, int T_in_total, int H, int W, int Cin, const CUtensorMap& tw, const GemmParams& p,
+                              cudaStream_t stream, const CUtensorMap* tx2);
+
+// 0: off; 1: W-reuse tiles (256 x 1 pixels) for swap-AB convs whose rows split into 256-pixel segments with <= 4 % waste
+static int g_conv_wr = -1, g_conv_wr_bo = -1;
+static int conv_wr_mode() {
+  if (g_conv_wr < 0) {
+    const char* e = getenv("SVR2_CONV_WR");
+    g_conv_wr = e ? atoi(e) : 1;
+    const char* b = getenv("SVR2_CONV_WR_BO");
+    g_conv_wr_bo = b ? atoi(b) : 1;
+  }
+  return g_conv_wr;
+}
 static void conv_tile_shape(int Cout, int H_out, int W_out, bool* swap_out, int* bw_out, int* bh_out) {
   const bool swap = (Cout > 64 && Cout <= 128) && (long long)H_out * W_out >= 256;
   int bw = 16, bh = 8;
@@ -1388,6 +1647,10 @@ static void conv_tile_shape(int Cout, int H_out, int W_out, bool* swap_out, int*
     bw = 32; bh = 8;
     if (W_out <= 16) { bw = 16; bh = 16; }
     if (W_out <= 8) { bw = 8; bh = 32; }
+    const int seg = (W_out + 255) / 256;
+    if (conv_wr_mode() && W_out >= 256 && (conv_wr_mode() == 2 || (long long)seg * 256 * 100 <= (long long)W_out * 104)) {
+      bw = 256; bh = 1;      // SVR2_CONV_WR=2: whenever a row holds one segment (tests of the ragged last segment)
+    }
   } else {
     if (W_out >= 128 && H_out < 8) { bw = 128; bh = 1; }
     else if (W_out <= 8) { bw = 8; bh = 16; }
@@ -1488,8 +1751,33 @@ static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, con
     p.stat_partial = (float4*)stat_partial;
     p.stat_slots = slots;
   }
+  if (swap && bw == 256 && bh == 1 && stride_hw == 1 && kh == 3 && kw == 3 && pad_hw == 1 && Cout <= 128 && Cout % 8 == 0)
+    return launch_conv_wreuse(x, T_in_total, H, W, Cin, tb, p, (cudaStream_t)stream, x2 ? &ta2 : nullptr);
   if (swap) return launch_gemm<256, KIND_BF16, true>(ta, tb, p, (cudaStream_t)stream, x2 ? &ta2 : nullptr);
   return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream, pair, x2 ? &ta2 : nullptr);
+}
+
+static int launch_conv_wreuse(const void* x, int T_in_total, int H, int W, int Cin, const CUtensorMap& tw, const GemmParams& p,
+                              cudaStream_t stream, const CUtensorMap* tx2) {
+  CUtensorMap tx, tail;
+  uint64_t d[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)T_in_total};
+  uint64_t s[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+  uint32_t b_row[4] = {BLOCK_K, 256, 1, 1}, b_tail[4] = {BLOCK_K, 8, 1, 1};
+  int rc = make_tmap_bf16(&tx, x, 4, d, s, b_row);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tail, x, 4, d, s, b_tail);
+  if (rc) return rc;
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wreuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WrSmem::kTotal);
+    if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
+    configured[dev] = true;
+  }
+  const int grid = p.num_m_tiles < num_sms() ? p.num_m_tiles : num_sms();
+  if (grid <= 0) return SVR2_OK;
+  conv_wreuse_kernel<<<grid, kNumThreads, WrSmem::kTotal, stream>>>(tx, tail, tw, tx2 ? *tx2 : tx, p, g_conv_wr_bo);
+  return check_launch("conv_wreuse");
 }
 
 // Upsample3D: 1x1x1 conv (GEMM over voxels) with the 3-D pixel shuffle fused into the store.

@@ -119,6 +119,10 @@ def _to_ndhwc(x_ncdhw, halo):
     (128, 128, (1, 3, 3), 1, 2, 2, 40, 72),      # swap-AB, spatial-only downsample
     (256, 128, (3, 3, 3), 1, 1, 2, 30, 44),      # swap-AB, ragged tile edges
     (128, 128, (1, 1, 1), 1, 1, 2, 24, 40),      # swap-AB 1x1x1
+    (128, 128, (3, 3, 3), 1, 1, 3, 9, 256),      # W-reuse kernel: one 256-pixel row segment per tile, 3 kw taps per load
+    (256, 128, (3, 3, 3), 1, 1, 2, 5, 520),      # W-reuse: three segments, ragged last one (8 valid pixels)
+    (128, 96, (1, 3, 3), 1, 1, 2, 6, 512),       # W-reuse: kt = 1, Cout < 128
+    (128, 128, (1, 3, 3), 1, 2, 2, 8, 1024),     # 256 x 1 tiles on the generic swap-AB kernel (stride 2: not eligible)
 ])
 def test_conv3d(svr2lib, Cin, Cout, k, st, shw, T, H, W):
     x = rnd(1, Cin, T, H, W, seed=1)
@@ -149,6 +153,7 @@ def test_conv3d(svr2lib, Cin, Cout, k, st, shw, T, H, W):
     (256, 512, 256, 3, 24, 40),     # decoder up2.res0: CTA pair
     (256, 128, 256, 2, 17, 33),     # encoder down1.res0 (odd sizes)
     (512, 256, 512, 1, 9, 16),      # encoder down2.res0, single frame
+    (128, 256, 128, 2, 7, 512),     # W-reuse kernel with the shortcut's extra k-blocks
 ])
 def test_conv3d_fused_shortcut(svr2lib, Cin, C2, Cout, T, H, W):
     """conv2(h) + conv_shortcut(x) as one contraction over [h ; x] (ResnetBlock3D, attn_video_vae.py:311-362) vs torch:

@@ -17,6 +17,14 @@ for s in $STAGES; do
     bench7b)  timeout 600 python bench.py --workload 4k_shard_7b --steps 3 --warmup 2 --phases --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_4k_shard_7b.json 2> gpurun_out/r2_bench_4k_shard_7b_phases.txt; cut -c1-500 gpurun_out/r2_bench_4k_shard_7b.json ;;
     clip64)   timeout 900 python bench.py --workload 4k_clip64 --steps 2 --warmup 1 --phases --lib-baseline none --no-cpu-baseline --no_graph > gpurun_out/r2_bench_4k_clip64.json 2> gpurun_out/r2_bench_4k_clip64_phases.txt; cut -c1-500 gpurun_out/r2_bench_4k_clip64.json ;;
     sweep)    for T in 16 32 64 128; do timeout 600 python bench.py --workload vae_decode_T$T --steps 3 --warmup 2 --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_vae_decode_T$T.json 2> gpurun_out/r2_bench_vae_decode_T$T.err; cut -c1-330 gpurun_out/r2_bench_vae_decode_T$T.json; echo; done ;;
+    sweep2)   for T in 16 128; do timeout 600 python bench.py --workload vae_decode_T$T --steps 2 --warmup 1 --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_vae_decode_T$T.json 2> gpurun_out/r2_bench_vae_decode_T$T.err; cut -c1-330 gpurun_out/r2_bench_vae_decode_T$T.json; echo; done ;;
+    ab_wr)    for cfg in "SVR2_CONV_WR=0" "SVR2_CONV_WR=2 SVR2_CONV_WR_BO=0" "SVR2_CONV_WR=2 SVR2_CONV_WR_BO=1"; do
+                echo "--- $cfg"; env $cfg timeout 300 python -m pytest tests/test_ops_gpu.py -q -x -k "conv3d" 2>&1 | tail -4
+                for i in 1 2 3; do env $cfg python tools/perf_conv_one.py conv128 2>&1 | tail -1; done
+              done 2>&1 | tee gpurun_out/r2_ab_wr.log
+              for v in 0 1; do echo "--- SVR2_ATTN_POLY=$v"; SVR2_ATTN_POLY=$v timeout 300 python -m pytest tests/test_ops_gpu.py -q -k "attn" 2>&1 | tail -2
+                for i in 1 2 3; do SVR2_ATTN_POLY=$v python tools/perf_conv_one.py attn 2>&1 | tail -1; done
+              done 2>&1 | tee gpurun_out/r2_ab_attn.log ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2_launches.csv python bench.py --workload 1080p --steps 1 --warmup 1 --no_graph --lib-baseline none --no-cpu-baseline > gpurun_out/r2_launches_bench.log 2>&1; tail -2 gpurun_out/r2_launches_bench.log | cut -c1-300 ;;
     ncu_conv) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -c 1 -f -o gpurun_out/r2_conv256 python tools/perf_conv_one.py conv256 > gpurun_out/r2_ncu_conv256.log 2>&1; tail -2 gpurun_out/r2_ncu_conv256.log ;;
     debug_native) timeout 300 python tools/debug_native.py > gpurun_out/r2_debug_native.log 2>&1; cat gpurun_out/r2_debug_native.log | tail -14 ;;
