@@ -1083,7 +1083,7 @@ static_assert(WrSmem::kTotal <= 232448, "W-reuse conv: shared memory budget");
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_wreuse_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x_tail,
                    const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x2,
-                   const GemmParams p, const int bo_mode) {
+                   const GemmParams p) {
   using L = WrSmem;
   constexpr int ACC_STRIDE = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -1187,10 +1187,11 @@ conv_wreuse_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             mbar_wait(&a_full[as], aph);
             tc_fence_after();
             const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem + L::kAOffset + as * L::kABytes));
-            // the tap's 256 operand rows start kw rows (of 128 B) into the stage; base offset = the start row's phase
-            // inside the 8-row swizzle atom
-            uint64_t b_desc = umma_desc_kmajor_sw128(b_addr + kw_ * 128);
-            if (bo_mode) b_desc |= static_cast<uint64_t>(kw_) << 49;
+            // the tap's 256 operand rows start kw rows (of 128 B) into the stage.  The 128B swizzle is a function of the
+            // absolute shared-memory address (bits 4-6 ^= bits 7-9) for TMA writes and UMMA reads alike, so a start address
+            // that is not 1024-aligned needs nothing else: the descriptor's base-offset field stays 0 (setting it to the
+            // start row's phase was measured to read the wrong chunks).
+            const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr + kw_ * 128);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, first ? 0u : 1u);
@@ -1629,17 +1630,17 @@ extern "C" int svr2_conv3d_shortcut_stats_bf16(const void* x, int T_in_total, in
 static int launch_conv_wreuse(const void* x, int T_in_total, int H, int W, int Cin, const CUtensorMap& tw, const GemmParams& p,
                               cudaStream_t stream, const CUtensorMap* tx2);
 
-// 0: off; 1: W-reuse tiles (256 x 1 pixels) for swap-AB convs whose rows split into 256-pixel segments with <= 4 % waste
-static int g_conv_wr = -1, g_conv_wr_bo = -1;
+// SVR2_CONV_WR / svr2_set_conv_wreuse: 0 off; 1 (default) W-reuse tiles (256 x 1 pixels) for swap-AB convs whose rows split
+// into 256-pixel segments with <= 4 % waste; 2 whenever a row holds a segment (tests of the ragged last segment)
+static int g_conv_wr = -1;
 static int conv_wr_mode() {
   if (g_conv_wr < 0) {
     const char* e = getenv("SVR2_CONV_WR");
     g_conv_wr = e ? atoi(e) : 1;
-    const char* b = getenv("SVR2_CONV_WR_BO");
-    g_conv_wr_bo = b ? atoi(b) : 1;
   }
   return g_conv_wr;
 }
+extern "C" void svr2_set_conv_wreuse(int mode) { g_conv_wr = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 static void conv_tile_shape(int Cout, int H_out, int W_out, bool* swap_out, int* bw_out, int* bh_out) {
   const bool swap = (Cout > 64 && Cout <= 128) && (long long)H_out * W_out >= 256;
   int bw = 16, bh = 8;
@@ -1776,7 +1777,7 @@ static int launch_conv_wreuse(const void* x, int T_in_total, int H, int W, int C
   }
   const int grid = p.num_m_tiles < num_sms() ? p.num_m_tiles : num_sms();
   if (grid <= 0) return SVR2_OK;
-  conv_wreuse_kernel<<<grid, kNumThreads, WrSmem::kTotal, stream>>>(tx, tail, tw, tx2 ? *tx2 : tx, p, g_conv_wr_bo);
+  conv_wreuse_kernel<<<grid, kNumThreads, WrSmem::kTotal, stream>>>(tx, tail, tw, tx2 ? *tx2 : tx, p);
   return check_launch("conv_wreuse");
 }
 

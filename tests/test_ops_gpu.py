@@ -125,6 +125,8 @@ def _to_ndhwc(x_ncdhw, halo):
     (128, 128, (1, 3, 3), 1, 2, 2, 8, 1024),     # 256 x 1 tiles on the generic swap-AB kernel (stride 2: not eligible)
 ])
 def test_conv3d(svr2lib, Cin, Cout, k, st, shw, T, H, W):
+    if W >= 256:
+        svr2lib.load().svr2_set_conv_wreuse(2)        # W-reuse tiles also where the last row segment is mostly empty
     x = rnd(1, Cin, T, H, W, seed=1)
     w = rnd(Cout, Cin, *k, std=(Cin * k[0] * k[1] * k[2]) ** -0.5, seed=2)
     b = rnd(Cout, seed=3)
@@ -144,8 +146,18 @@ def test_conv3d(svr2lib, Cin, Cout, k, st, shw, T, H, W):
                    bias=bf(b), residual=torch.cat([res[:1], res[:1], res], 0).contiguous(), out_t_pad=2,
                    out_dup_head=1)
     ref_nd = bf(bf(ref[0].permute(1, 2, 3, 0)).float() + res.float())
+    svr2lib.load().svr2_set_conv_wreuse(1)
     assert_close(y[2:], ref_nd, 4e-3, "conv3d body")
     assert torch.equal(y[0], y[2]) and torch.equal(y[1], y[2]), "halo frames must replicate frame 0"
+    if W >= 256 and shw == 1 and k[1] == 3:           # the generic swap-AB kernel on the same problem: same products,
+        y0 = torch.zeros_like(y)                      # another summation order of the fp32 accumulation
+        svr2lib.load().svr2_set_conv_wreuse(0)
+        try:
+            svr2lib.conv3d(x_nd, T + halo, H, W, Cin, w_k, Cout, k, st, shw, 1, T_out, y0, bias=bf(b),
+                           residual=torch.cat([res[:1], res[:1], res], 0).contiguous(), out_t_pad=2, out_dup_head=1)
+        finally:
+            svr2lib.load().svr2_set_conv_wreuse(1)
+        assert_close(y, y0, 2e-3, "W-reuse kernel vs generic swap-AB kernel")
 
 
 @pytest.mark.parametrize("Cin,C2,Cout,T,H,W", [
