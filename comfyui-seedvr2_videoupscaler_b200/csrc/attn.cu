@@ -72,7 +72,11 @@ struct AttnParams {
 // POLY: three of every eight column pairs of a full tile take their exp2 on the FMA pipe (ptx.cuh exp2_poly, relative
 // error 5e-5 against the 4e-3 of the bf16 rounding that follows): the 64 ex2 per row and tile keep the MUFU pipe busy
 // exactly as long as the tile's two MMAs keep the tensor pipe (512 cycles each), and both of an SM's CTAs share it.
-template <bool POLY>
+// PTM: the probabilities go to tensor memory (tcgen05.st, 32 columns of packed bf16 pairs next to S) and P V is a
+// TS-MMA (A operand from TMEM) instead of st.shared + fence.proxy.async + an SS-MMA: the generic->async proxy fence and
+// the arrive behind it were 25 % of the softmax warps' stall samples (profiles/ncu_attn_r2.md); the barrier polls for
+// pv_done / the next s_full are issued early so that their round trip overlaps the exponentials / the P store.
+template <bool POLY, bool PTM>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -119,7 +123,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+  const uint32_t tmem_s = tmem_base, tmem_p = tmem_base + 64, tmem_o = tmem_base + 128;
 
   // work item w -> (q tile, head, sequence); q tiles of one (sequence, head) are neighbours so that the CTAs running
   // at the same time share its K / V through L2
@@ -215,9 +219,13 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < ATT_BN / 16; ++kk) {       // contraction over the 64 kv rows (16 per MMA)
-            const uint64_t da = umma_desc_kmajor_sw128(p_addr) + uint64_t(kk * 2);
             const uint64_t db = umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, ATT_KVH_BYTES, 1024);
-            umma_bf16(tmem_o, da, db, idesc_pv, (j | kk) != 0);
+            if constexpr (PTM) {
+              umma_bf16_ts(tmem_o, tmem_p + kk * 8, db, idesc_pv, (j | kk) != 0);
+            } else {
+              const uint64_t da = umma_desc_kmajor_sw128(p_addr) + uint64_t(kk * 2);
+              umma_bf16(tmem_o, da, db, idesc_pv, (j | kk) != 0);
+            }
           }
           umma_commit(v_empty);
           umma_commit(pv_done);
@@ -245,8 +253,9 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       if (qt * ATT_BM >= len) continue;
       const int n_kv = (len + ATT_BN - 1) / ATT_BN;
       float m_ref = -INFINITY, l_run = 0.f;
+      bool s_ok = false;                          // PTM: s_full of this tile already seen complete by the early poll
       for (int j = 0; j < n_kv; ++j, ++g) {
-        mbar_wait(s_full, g & 1);
+        if (!(PTM && s_ok)) mbar_wait(s_full, g & 1);
         tc_fence_after();
         uint32_t sv[ATT_BN];
         tmem_ld32(tmem_s + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
@@ -272,6 +281,10 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             mx4[a] = fmaxf(fmaxf(mx4[a], __uint_as_float(sv[c + a])), __uint_as_float(sv[(c + 4 + a) & (ATT_BN - 1)]));
         }
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        bool pv_ok = false;
+        if constexpr (PTM) {
+          if (j > 0) pv_ok = mbar_try_wait(pv_done, (g - 1) & 1);     // round trip hidden behind the exponentials
+        }
         const bool grow = (mx - m_ref) * sc > kGrow;                   // true on the first tile (m_ref = -inf)
         const float m_new = grow ? mx : m_ref;
         const float alpha = grow ? fast_exp2((m_ref - m_new) * sc) : 1.0f;   // 0 on the first tile
@@ -301,7 +314,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         const float lsum = (ls[0].x + ls[1].x) + (ls[0].y + ls[1].y);
         if (j > 0) {
-          mbar_wait(pv_done, (g - 1) & 1);        // P_{j-1} V_{j-1} has read the P buffer and updated O
+          if (!(PTM && pv_ok)) mbar_wait(pv_done, (g - 1) & 1);   // P_{j-1} V_{j-1} has read the P buffer and updated O
           tc_fence_after();
           if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
@@ -318,15 +331,26 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             tmem_st_wait();
           }
         }
-        // P -> swizzled K-major smem (row = this thread, 8 chunks of 16 B); explicit shared-space stores
+        if constexpr (PTM) {
+          // P -> tensor memory: this thread's row, 32 columns of packed pairs (keys 2c, 2c + 1 in column c)
+          tmem_st32(tmem_p + lane_off, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+          l_run = l_run * alpha + lsum;
+          m_ref = m_new;
+          s_ok = (j + 1 < n_kv) && mbar_try_wait(s_full, (g + 1) & 1);   // next scores: poll behind the store's wait
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(p_ready);
+        } else {
+          // P -> swizzled K-major smem (row = this thread, 8 chunks of 16 B); explicit shared-space stores
 #pragma unroll
-        for (int ch = 0; ch < ATT_BN / 8; ++ch)
-          st_shared_v4(sp_row + ((ch ^ (row & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-        l_run = l_run * alpha + lsum;
-        m_ref = m_new;
-        fence_proxy_async_smem();                  // make P visible to the tensor core (async proxy)
-        tc_fence_before();
-        mbar_arrive(p_ready);
+          for (int ch = 0; ch < ATT_BN / 8; ++ch)
+            st_shared_v4(sp_row + ((ch ^ (row & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          l_run = l_run * alpha + lsum;
+          m_ref = m_new;
+          fence_proxy_async_smem();                  // make P visible to the tensor core (async proxy)
+          tc_fence_before();
+          mbar_arrive(p_ready);
+        }
       }
       // ------------------------------ epilogue: O / l -> bf16 -> global
       mbar_wait(pv_done, (g - 1) & 1);
@@ -378,16 +402,20 @@ extern "C" int svr2_attn_varlen_bf16(const void* q, const void* k, const void* v
   if (n_seq <= 0 || total <= 0) return SVR2_OK;
   if (max_seqlen <= 0) return set_error(SVR2_ERR_ARG, "svr2_attn_varlen_bf16: max_seqlen must be > 0");
   static bool configured[64] = {};                // the attribute is per (function, device)
-  static int poly = -1;                           // SVR2_ATTN_POLY=1: part of the exp2 on the FMA pipe (A/B switch)
+  // A/B switches: SVR2_ATTN_POLY=1 part of the exp2 on the FMA pipe (measured slower: 0.878 vs 0.842 ms on 243 x 463 x 20);
+  // SVR2_ATTN_PTMEM=0 the probabilities through shared memory (the round-1 / early round-2 path)
+  static int poly = -1, ptm = -1;
   if (poly < 0) {
     const char* e = getenv("SVR2_ATTN_POLY");
     poly = e ? atoi(e) : 0;
+    const char* t = getenv("SVR2_ATTN_PTMEM");
+    ptm = t ? atoi(t) : 1;
   }
+  auto kern = ptm ? (poly ? attn_varlen_kernel<true, true> : attn_varlen_kernel<false, true>)
+                  : (poly ? attn_varlen_kernel<true, false> : attn_varlen_kernel<false, false>);
   const int dev = current_device();
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_varlen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_varlen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kTotal);
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
     configured[dev] = true;
   }
@@ -412,7 +440,6 @@ extern "C" int svr2_attn_varlen_bf16(const void* q, const void* k, const void* v
   if (n_work > 0x7fffffffLL) return set_error(SVR2_ERR_ARG, "svr2_attn_varlen_bf16: too many work items");
   p.n_work = (int)n_work;
   const int grid = (int)(n_work < 2LL * num_sms() ? n_work : 2LL * num_sms());   // persistent: two CTAs per SM
-  if (poly) attn_varlen_kernel<true><<<grid, ATT_THREADS, AttnSmem::kTotal, (cudaStream_t)stream>>>(tq, tk, tv, p);
-  else attn_varlen_kernel<false><<<grid, ATT_THREADS, AttnSmem::kTotal, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  kern<<<grid, ATT_THREADS, AttnSmem::kTotal, (cudaStream_t)stream>>>(tq, tk, tv, p);
   return check_launch("attn_varlen");
 }

@@ -1117,6 +1117,14 @@ conv_wreuse_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   const int num_tiles = p.num_m_tiles;                 // one n-tile: Cout <= 128
   const int taps_t = p.taps_t, cin_blocks = p.cin_blocks, extra = p.extra_blocks;
   const int n_groups = taps_t * 3 * cin_blocks;        // (kt, kh, cb) activation stages of three k-blocks each
+  // The shortcut's single-k-block stages are spread evenly between the regular groups (shortcut block e after
+  // max(1, (e + 1) * n_groups / (extra + 1)) regular groups): back to back at the end of a tile they would shrink the activation ring's
+  // lookahead from 3 x 1536 to 3 x 512 MMA cycles, less than a TMA round trip.  All three roles walk the same schedule.
+  auto extras_after = [&](int gi, int e) {
+    if (e >= extra) return false;
+    const int pos = (e + 1) * n_groups / (extra + 1);       // in [0, n_groups): after that many regular groups, at least one
+    return (pos < 1 ? 1 : pos) == gi + 1;
+  };
 
   if (warp == 0) {
     // ------------------------- activation rows: one stage per (kt, kh, cb) + one per shortcut block
@@ -1127,25 +1135,26 @@ conv_wreuse_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         int t_o, th, tw;
         conv_tile(p, tile, t_o, th, tw);
         const int w0 = tw * 256;
+        int gi = 0, e = 0;
         for (int kt_ = 0; kt_ < taps_t; ++kt_) {
           const int t_in = t_o * p.stride_t + kt_;
           for (int kh_ = 0; kh_ < 3; ++kh_) {
             const int h_in = th + kh_ - 1;
-            for (int cb = 0; cb < cin_blocks; ++cb) {
+            for (int cb = 0; cb < cin_blocks; ++cb, ++gi) {
               mbar_wait(&b_empty[stage], phase ^ 1);
               uint8_t* sb = smem + stage * L::kBBytes;
               mbar_expect_tx(&b_full[stage], L::kBBytes);
               tma_load_4d(sb, &tmap_x, &b_full[stage], cb * BLOCK_K, w0 - 1, h_in, t_in);
               tma_load_4d(sb + 256 * 128, &tmap_x_tail, &b_full[stage], cb * BLOCK_K, w0 + 255, h_in, t_in);
               if (++stage == L::kNB) { stage = 0; phase ^= 1; }
+              for (; extras_after(gi, e); ++e) {        // fused 1x1x1 shortcut: the block input at the output pixels
+                mbar_wait(&b_empty[stage], phase ^ 1);
+                mbar_expect_tx(&b_full[stage], 256 * 128);
+                tma_load_4d(smem + stage * L::kBBytes, &tmap_x2, &b_full[stage], e * BLOCK_K, w0, th, t_o);
+                if (++stage == L::kNB) { stage = 0; phase ^= 1; }
+              }
             }
           }
-        }
-        for (int cb = 0; cb < extra; ++cb) {            // fused 1x1x1 shortcut: the block input at the output pixels
-          mbar_wait(&b_empty[stage], phase ^ 1);
-          mbar_expect_tx(&b_full[stage], 256 * 128);
-          tma_load_4d(smem + stage * L::kBBytes, &tmap_x2, &b_full[stage], cb * BLOCK_K, w0, th, t_o);
-          if (++stage == L::kNB) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -1162,10 +1171,12 @@ conv_wreuse_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         if (++stage == L::kNA) { stage = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int gi = 0, e = 0;
         for (int g = 0; g < taps_t * 3; ++g)            // g = kt * 3 + kh
-          for (int cb = 0; cb < cin_blocks; ++cb)
+          for (int cb = 0; cb < cin_blocks; ++cb, ++gi) {
             for (int kw_ = 0; kw_ < 3; ++kw_) load((g * 3 + kw_) * cin + cb * BLOCK_K);
-        for (int cb = 0; cb < extra; ++cb) load(taps_t * 9 * cin + cb * BLOCK_K);
+            for (; extras_after(gi, e); ++e) load(taps_t * 9 * cin + e * BLOCK_K);
+          }
       }
     }
   } else if (warp == 1) {
@@ -1179,8 +1190,12 @@ conv_wreuse_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
         uint32_t first = 1;
+        int gi = 0, e = 0;
         for (int g = 0; g < n_groups + extra; ++g) {
-          const int n_taps = g < n_groups ? 3 : 1;
+          // stage g of the tile's schedule: a regular group (three taps) or, after group gi - 1, a shortcut block
+          const bool is_extra = gi > 0 && extras_after(gi - 1, e);
+          const int n_taps = is_extra ? 1 : 3;
+          if (is_extra) ++e; else ++gi;
           mbar_wait(&b_full[bs], bph);
           const uint32_t b_addr = smem_u32(smem + bs * L::kBBytes);
           for (int kw_ = 0; kw_ < n_taps; ++kw_) {
@@ -1727,6 +1742,11 @@ static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, con
     long long bhn = (12LL << 20) / (row_bytes > 0 ? row_bytes : 1);
     if (bhn < 1) bhn = 1;
     if (bhn > (H_out + bh - 1) / bh) bhn = (H_out + bh - 1) / bh;
+    if (bw == 256 && bh == 1) {     // one-row tiles: 8 MB of input rows per frame (12 MB measured 1.6 x the DRAM reads)
+      bhn = (8LL << 20) / (row_bytes > 0 ? row_bytes : 1);
+      if (bhn < 2) bhn = 2;
+      if (bhn > H_out) bhn = H_out;
+    }
     p.band_h = (kt > 1) ? (int)bhn : (H_out + bh - 1) / bh;   // no temporal reuse for kt = 1: plain frame-major order
   }
   p.M = T_out * p.tiles_w * p.tiles_h * BLOCK_M;

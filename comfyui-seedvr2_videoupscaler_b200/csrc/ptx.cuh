@@ -199,6 +199,17 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a,
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M x 16 bf16, K-major) is read from tensor memory — lane = row, 8 columns of
+// packed bf16 pairs per K = 16 step (what tcgen05.st.32x32b of packed registers lays down).  Single CTA, one thread issues.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // commit: arrive on the barrier at this offset in BOTH CTAs once the pair's MMAs have completed
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
   asm volatile(

@@ -27,6 +27,13 @@ for s in $STAGES; do
               done 2>&1 | tee gpurun_out/r2_ab_attn.log ;;
     ncu_wr)   timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_wreuse -c 1 -f -o gpurun_out/r2_conv_wr python tools/perf_conv_one.py conv128 > gpurun_out/r2_ncu_conv_wr.log 2>&1; tail -2 gpurun_out/r2_ncu_conv_wr.log
               SVR2_CONV_WR=0 timeout 600 ncu --set full --clock-control none -k regex:gemm_tcgen05 -c 1 -f -o gpurun_out/r2_conv128_generic python tools/perf_conv_one.py conv128 > gpurun_out/r2_ncu_conv128_generic.log 2>&1; tail -2 gpurun_out/r2_ncu_conv128_generic.log ;;
+    ab_wr2)   for cfg in "SVR2_CONV_WR=0" "SVR2_CONV_WR=1"; do echo "--- $cfg"
+                for c in conv128 conv_sc; do for i in 1 2; do env $cfg PERF_REPS=10 python tools/perf_conv_one.py $c 2>&1 | tail -1; done; done
+              done 2>&1 | tee gpurun_out/r2_ab_wr2.log
+              timeout 300 python -m pytest tests/test_ops_gpu.py -q -x -k "conv3d" 2>&1 | tail -3 ;;
+    ab_attn2) for v in 0 1; do echo "--- SVR2_ATTN_PTMEM=$v"; SVR2_ATTN_PTMEM=$v timeout 300 python -m pytest tests/test_ops_gpu.py tests/test_models_gpu.py -q -k "attn or attention or dit_vs_golden" 2>&1 | tail -3
+                for i in 1 2 3; do SVR2_ATTN_PTMEM=$v PERF_REPS=20 python tools/perf_conv_one.py attn 2>&1 | tail -1; done
+              done 2>&1 | tee gpurun_out/r2_ab_attn2.log ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2_launches.csv python bench.py --workload 1080p --steps 1 --warmup 1 --no_graph --lib-baseline none --no-cpu-baseline > gpurun_out/r2_launches_bench.log 2>&1; tail -2 gpurun_out/r2_launches_bench.log | cut -c1-300 ;;
     ncu_conv) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -c 1 -f -o gpurun_out/r2_conv256 python tools/perf_conv_one.py conv256 > gpurun_out/r2_ncu_conv256.log 2>&1; tail -2 gpurun_out/r2_ncu_conv256.log ;;
     debug_native) timeout 300 python tools/debug_native.py > gpurun_out/r2_debug_native.log 2>&1; cat gpurun_out/r2_debug_native.log | tail -14 ;;

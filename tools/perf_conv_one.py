@@ -16,6 +16,15 @@ elif which == "conv128":    # swap-AB kernel, 128 -> 128 at 2 x 2160 x 3840
     T, H, W, C = 2, 2160, 3840, 128
     x = rnd(T + 2, H, W, C); w = rnd(C, 27 * C) * 0.01; b = rnd(C); y = torch.empty(T, H, W, C, device=dev, dtype=torch.bfloat16)
     fn = lambda: lib.conv3d(x, T + 2, H, W, C, w, C, (3, 3, 3), 1, 1, 1, T, y, bias=b)
+elif which == "conv_sc":    # ResnetBlock3D conv2 + fused 1x1x1 shortcut, 128 (+256) -> 128 at 2 x 2160 x 3840
+    import ctypes
+    T, H, W, C, C2 = 2, 2160, 3840, 128, 256
+    x = rnd(T + 2, H, W, C); x2 = rnd(T, H, W, C2); w = rnd(C, 27 * C + C2) * 0.01; b = rnd(C)
+    y = torch.empty(T, H, W, C, device=dev, dtype=torch.bfloat16)
+    slots = ctypes.c_int(lib.load().svr2_conv_stat_slots(C, H, W))
+    part = torch.empty(T * slots.value * (C // 8) * 4, device=dev, dtype=torch.float32)
+    fn = lambda: lib.call("svr2_conv3d_shortcut_stats_bf16", lib.ptr(x), T + 2, H, W, C, lib.ptr(w), C, 3, 3, 3, T, lib.ptr(b),
+                          lib.ptr(x2), C2, lib.ptr(y), 0, 0, lib.ptr(part), part.numel() * 4, ctypes.byref(slots), lib.stream())
 elif which == "swiglu":     # DiT SwiGLU input projection at the 4K shard (L = 97200)
     L = 97200
     a = rnd(L, 2560); w = rnd(13824, 2560) * 0.02
@@ -39,5 +48,8 @@ elif which == "shortcut":   # 1x1x1 conv_shortcut 256 -> 128 at 2 x 2160 x 3840 
 for _ in range(3): fn()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-print(which, f"{e0.elapsed_time(e1):.3f} ms")
+n = int(os.environ.get("PERF_REPS", "1"))
+e0.record()
+for _ in range(n): fn()
+e1.record(); torch.cuda.synchronize()
+print(which, f"{e0.elapsed_time(e1) / n:.3f} ms")
