@@ -42,6 +42,9 @@ for s in $STAGES; do
     mgpu8)    TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
               timeout 900 $TR bench.py --gpus 8 --workload 4k_shard_7b --steps 3 --warmup 2 --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_4k_shard_7b_n8.json 2> gpurun_out/r2_bench_4k_shard_7b_n8.err; cut -c1-400 gpurun_out/r2_bench_4k_shard_7b_n8.json
               for T in 16 128; do timeout 900 $TR bench.py --gpus 8 --workload vae_decode_T$T --steps 2 --warmup 1 --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_vae_decode_T${T}_n8.json 2> gpurun_out/r2_bench_vae_decode_T${T}_n8.err; cut -c1-330 gpurun_out/r2_bench_vae_decode_T${T}_n8.json; echo; done ;;
+    mgpu8b)   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
+              timeout 600 $TR bench.py --gpus 8 --workload 4k_shard_7b --steps 2 --warmup 1 --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_4k_shard_7b_n8.json 2> gpurun_out/r2_bench_4k_shard_7b_n8.err; cut -c1-400 gpurun_out/r2_bench_4k_shard_7b_n8.json; echo
+              timeout 600 $TR bench.py --gpus 8 --workload vae_decode_T128 --steps 1 --warmup 1 --lib-baseline none --no-cpu-baseline > gpurun_out/r2_bench_vae_decode_T128_n8.json 2> gpurun_out/r2_bench_vae_decode_T128_n8.err; cut -c1-330 gpurun_out/r2_bench_vae_decode_T128_n8.json; echo ;;
     perf_up)  timeout 300 python tools/perf_upsample.py 2>&1 | tee gpurun_out/r2_perf_upsample.log ;;
     *) echo "unknown stage $s" ;;
   esac
