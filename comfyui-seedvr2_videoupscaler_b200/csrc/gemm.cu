@@ -224,11 +224,20 @@ __device__ __forceinline__ RowDest row_dest(const GemmParams& p, int epi, int m_
 // EPI_CT >= 0: the epilogue flags are a compile-time constant (p.epi must equal it) — the per-element loops then carry
 // no runtime flag tests.  A single such test cost the short-K pixel-shuffle GEMM 50 % (its epilogue, ~1 800 warp
 // instructions per tile, is the whole kernel); EPI_CT = -1 keeps the generic runtime-flag epilogue.
-template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false, int EPI_CT = -1>
+// WR (CTA pairs, stride-1 3x3-spatial convs only): W-reuse mainloop — an m-tile is ONE output row segment of 128 pixels per
+// CTA, so the three horizontal taps of a (kt, kh, 64-channel block) read the same 130-pixel input row segment: it is loaded
+// once (boxes of 128 + 8 pixels into a 17 KB stage) and the taps' MMAs address it through A descriptors whose start is
+// shifted by kw rows of 128 B (see conv_wreuse_kernel).  Activation traffic per SM drops 3x: 21.7 KB instead of 32 KB of
+// operands per k-block — these kernels run at 97 % tensor-pipe activity but power-capped far below the boost clock, and
+// L2 -> SM operand traffic is a large part of that power.  Two rings: kWrNA activation stages, kWrNB weight k-blocks.
+constexpr int kWrNA = 4, kWrNB = 7, kWrABytes = 136 * 128;
+template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false, int EPI_CT = -1, bool WR = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_a2, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_a_tail,
+                    const GemmParams p) {
   static_assert(!(SWAP && TWO), "swap-AB and CTA pairs are mutually exclusive");
+  static_assert(!WR || (TWO && BLOCK_N == 256 && KIND == KIND_BF16), "the W-reuse mainloop exists for the CTA-pair bf16 conv kernel");
   if (p.run_if != nullptr && *p.run_if == 0) return;     // conditional launch: every thread of every CTA sees the same flag
   using L = SmemLayout<BLOCK_N, TWO>;
   const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
@@ -240,7 +249,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;
+  // WR: full_bar = [activation stages | weight stages], empty_bar likewise
+  constexpr int kBars = WR ? kWrNA + kWrNB : kStages;
+  if constexpr (WR) empty_bar = full_bar + kBars;
+  static_assert(!WR || (kWrNA * kWrABytes + kWrNB * (BLOCK_N / 2) * BLOCK_K * 2 <= L::kStagingOffset && 2 * kBars + 5 <= 32),
+                "W-reuse rings must fit the generic kernel's operand region and barrier block");
+  uint64_t* tmem_full = empty_bar + kBars;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -253,7 +267,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (p.extra_blocks) tma_prefetch_desc(&tmap_a2);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kBars; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -280,7 +294,140 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int tile0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
-  if (warp == 0 || warp == 3) {
+  // W-reuse schedule shared by the three roles: (kt, kh, cb) groups of three k-blocks (kw = 0, 1, 2), the fused shortcut's
+  // single-k-block stages spread evenly between them (see conv_wreuse_kernel)
+  const int wr_groups = p.taps_t * 3 * p.cin_blocks;
+  auto wr_extras_after = [&](int gi, int e) {
+    if (e >= p.extra_blocks) return false;
+    const int pos = (e + 1) * wr_groups / (p.extra_blocks + 1);
+    return (pos < 1 ? 1 : pos) == gi + 1;
+  };
+  if (WR && warp == 0) {
+    // ------------------------- W-reuse: activation row segments, one stage per (kt, kh, cb) + one per shortcut block
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto acquire = [&](uint32_t bytes) -> uint8_t* {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * bytes);         // both CTAs' bytes land on CTA 0's barrier
+        return smem + stage * kWrABytes;
+      };
+      auto advance = [&]() { if (++stage == kWrNA) { stage = 0; phase ^= 1; } };
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        int m_sup, n_blk;
+        tile_coords(tile, num_m_sup, num_n_tiles, p.group_n, m_sup, n_blk);
+        int t_o, th, tw;
+        conv_tile(p, 2 * m_sup + (int)cta_rank, t_o, th, tw);
+        const int w0 = tw * 128;
+        int gi = 0, e = 0;
+        for (int kt_ = 0; kt_ < p.taps_t; ++kt_) {
+          const int t_in = t_o * p.stride_t + kt_;
+          for (int kh_ = 0; kh_ < 3; ++kh_) {
+            const int h_in = th + kh_ - 1;
+            for (int cb = 0; cb < p.cin_blocks; ++cb, ++gi) {
+              uint8_t* sa = acquire(kWrABytes);
+              tma2_load_4d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, w0 - 1, h_in, t_in);
+              tma2_load_4d(sa + 128 * 128, &tmap_a_tail, &full_bar[stage], cb * BLOCK_K, w0 + 127, h_in, t_in);
+              advance();
+              for (; wr_extras_after(gi, e); ++e) {      // fused 1x1x1 shortcut: the block input at the output pixels
+                uint8_t* sx = acquire(128 * 128);
+                tma2_load_4d(sx, &tmap_a2, &full_bar[stage], e * BLOCK_K, w0, th, t_o);
+                advance();
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (WR && (warp == 3 || warp == 2)) {
+    // ------------------------- W-reuse: this CTA's half of the weight rows, one stage per k-block, in MMA order.  Two
+    // threads (warp 3: even k-blocks, warp 2 — the TMEM allocator, idle in the main loop — odd ones): one producer
+    // iteration (barrier poll, expect-tx, TMA issue) costs ~500 cycles, the k-block's MMAs 512
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t turn = warp == 3 ? 0u : 1u;
+      constexpr int kWBytes = (BLOCK_N / 2) * BLOCK_K * 2;
+      uint8_t* wbase = smem + kWrNA * kWrABytes;
+      const int cin = p.cin;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        int m_sup, n_blk;
+        tile_coords(tile, num_m_sup, num_n_tiles, p.group_n, m_sup, n_blk);
+        const int n0 = n_blk * BLOCK_N + (int)cta_rank * (BLOCK_N / 2);
+        auto load = [&](int kcol) {
+          if ((turn++ & 1u) == 0u) {
+            mbar_wait(&empty_bar[kWrNA + stage], phase ^ 1);
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[kWrNA + stage], 2 * kWBytes);
+            tma2_load_2d(wbase + stage * kWBytes, &tmap_b, &full_bar[kWrNA + stage], kcol, n0);
+          }
+          if (++stage == kWrNB) { stage = 0; phase ^= 1; }
+        };
+        int gi = 0, e = 0;
+        for (int g = 0; g < p.taps_t * 3; ++g)            // g = kt * 3 + kh
+          for (int cb = 0; cb < p.cin_blocks; ++cb, ++gi) {
+            for (int kw_ = 0; kw_ < 3; ++kw_) load((g * 3 + kw_) * cin + cb * BLOCK_K);
+            for (; wr_extras_after(gi, e); ++e) load(p.taps_t * 9 * cin + e * BLOCK_K);
+          }
+      }
+    }
+  } else if (WR && warp == 1) {
+    // ------------------------- W-reuse: MMA issuer (CTA 0 of the pair)
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N);
+      constexpr int kWBytes = (BLOCK_N / 2) * BLOCK_K * 2;
+      const uint32_t w_addr0 = smem_u32(smem + kWrNA * kWrABytes);
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        // The issuing thread is the critical resource (its per-k-block path — barrier poll, descriptor set-up, four
+        // UTCHMMA with their uniform-register moves, commit — measured 613 cycles against 512 of MMA work in the first
+        // version of this loop): constant-trip tap loop, descriptors advanced by additions, the shortcut schedule
+        // reduced to one comparison per group.
+        uint32_t first = 1;
+        int e = 0;
+        auto next_extra_pos = [&](int e_) {
+          if (e_ >= p.extra_blocks) return 0x7fffffff;
+          const int pos = (e_ + 1) * wr_groups / (p.extra_blocks + 1);
+          return pos < 1 ? 1 : pos;
+        };
+        int extra_pos = next_extra_pos(0);
+        auto taps = [&](const int n_taps) {
+          mbar_wait(&full_bar[as], aph);
+          const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(smem + as * kWrABytes));
+#pragma unroll
+          for (int kw_ = 0; kw_ < 3; ++kw_) {
+            if (kw_ < n_taps) {
+              mbar_wait(&full_bar[kWrNA + bs], bph);
+              tc_fence_after();
+              const uint64_t a_desc = a_desc0 + uint64_t(kw_ * 8);      // kw rows of 128 B into the stage (address-based swizzle)
+              const uint64_t b_desc = umma_desc_kmajor_sw128(w_addr0 + bs * kWBytes);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                umma_bf16_2cta(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit_2cta(&empty_bar[kWrNA + bs]);
+              if (++bs == kWrNB) { bs = 0; bph ^= 1; }
+            }
+          }
+          umma_commit_2cta(&empty_bar[as]);
+          if (++as == kWrNA) { as = 0; aph ^= 1; }
+        };
+        for (int gi = 0; gi < wr_groups; ++gi) {
+          taps(3);
+          while (extra_pos == gi + 1) {      // the shortcut blocks scheduled after this group
+            taps(1);
+            extra_pos = next_extra_pos(++e);
+          }
+        }
+        umma_commit_2cta(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp == 0 || warp == 3) {
     // ========================= TMA producers (2 warps) =========================
     // One thread of warp 0 feeds the even k-blocks of the ring, one thread of warp 3 the odd ones.
     // A single producer thread costs ~500 issue cycles per k-block (measured) against 512 cycles of
@@ -1067,8 +1214,9 @@ int num_sms() {
 // per k-block).  Two rings: NB activation stages (33 KB, three k-blocks each) fed by warp 0, NA weight stages (16 KB,
 // one k-block each) fed by warp 3; warp 1 issues, warp 2 owns TMEM, warps 4-11 run the swap-AB epilogue (bias,
 // residual, halo duplication, GroupNorm partial sums) of the generic kernel.
+template <int NB, int NA>
 struct WrSmem {
-  static constexpr int kNB = 3, kNA = 5;
+  static constexpr int kNB = NB, kNA = NA;
   static constexpr int kBRows = 264;                       // 256 + 2 halo pixels, rounded to whole 8-row swizzle atoms
   static constexpr int kBBytes = kBRows * 128;             // 33 792
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;    // 16 384
@@ -1078,13 +1226,13 @@ struct WrSmem {
   static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;
 };
-static_assert(WrSmem::kTotal <= 232448, "W-reuse conv: shared memory budget");
-
+template <int NB, int NA>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_wreuse_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x_tail,
                    const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x2,
                    const GemmParams p) {
-  using L = WrSmem;
+  using L = WrSmem<NB, NA>;
+  static_assert(L::kTotal <= 232448, "W-reuse conv: shared memory budget");
   constexpr int ACC_STRIDE = 256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1158,16 +1306,21 @@ conv_wreuse_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         }
       }
     }
-  } else if (warp == 3) {
-    // ------------------------- weight k-blocks, in the order the MMA warp consumes them
+  } else if (warp == 3 || warp == 2) {
+    // ------------------------- weight k-blocks, in the order the MMA warp consumes them.  Two threads (warp 3: even
+    // k-blocks, warp 2 — the TMEM allocator, idle in the main loop — odd ones): one producer iteration (barrier poll,
+    // expect-tx, TMA issue) costs ~500 cycles, the k-block's MMAs 512
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t turn = warp == 3 ? 0u : 1u;
       const int cin = p.cin;
       auto load = [&](int kcol) {
-        mbar_wait(&a_empty[stage], phase ^ 1);
-        mbar_expect_tx(&a_full[stage], L::kABytes);
-        tma_load_2d(smem + L::kAOffset + stage * L::kABytes, &tmap_w, &a_full[stage], kcol, 0);
+        if ((turn++ & 1u) == 0u) {
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          mbar_expect_tx(&a_full[stage], L::kABytes);
+          tma_load_2d(smem + L::kAOffset + stage * L::kABytes, &tmap_w, &a_full[stage], kcol, 0);
+        }
         if (++stage == L::kNA) { stage = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -1189,34 +1342,48 @@ conv_wreuse_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        // (the issuing thread is the critical resource: constant-trip tap loop, one comparison per group for the shortcut
+        // schedule — see the CTA-pair W-reuse loop)
         uint32_t first = 1;
-        int gi = 0, e = 0;
-        for (int g = 0; g < n_groups + extra; ++g) {
-          // stage g of the tile's schedule: a regular group (three taps) or, after group gi - 1, a shortcut block
-          const bool is_extra = gi > 0 && extras_after(gi - 1, e);
-          const int n_taps = is_extra ? 1 : 3;
-          if (is_extra) ++e; else ++gi;
+        int e = 0;
+        auto next_extra_pos = [&](int e_) {
+          if (e_ >= extra) return 0x7fffffff;
+          const int pos = (e_ + 1) * n_groups / (extra + 1);
+          return pos < 1 ? 1 : pos;
+        };
+        int extra_pos = next_extra_pos(0);
+        auto taps = [&](const int n_taps) {
           mbar_wait(&b_full[bs], bph);
-          const uint32_t b_addr = smem_u32(smem + bs * L::kBBytes);
-          for (int kw_ = 0; kw_ < n_taps; ++kw_) {
-            mbar_wait(&a_full[as], aph);
-            tc_fence_after();
-            const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem + L::kAOffset + as * L::kABytes));
-            // the tap's 256 operand rows start kw rows (of 128 B) into the stage.  The 128B swizzle is a function of the
-            // absolute shared-memory address (bits 4-6 ^= bits 7-9) for TMA writes and UMMA reads alike, so a start address
-            // that is not 1024-aligned needs nothing else: the descriptor's base-offset field stays 0 (setting it to the
-            // start row's phase was measured to read the wrong chunks).
-            const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr + kw_ * 128);
+          const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(smem + bs * L::kBBytes));
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, first ? 0u : 1u);
-              first = 0;
+          for (int kw_ = 0; kw_ < 3; ++kw_) {
+            if (kw_ < n_taps) {
+              mbar_wait(&a_full[as], aph);
+              tc_fence_after();
+              const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(smem + L::kAOffset + as * L::kABytes));
+              // the tap's 256 operand rows start kw rows (of 128 B) into the stage.  The 128B swizzle is a function of the
+              // absolute shared-memory address (bits 4-6 ^= bits 7-9) for TMA writes and UMMA reads alike, so a start address
+              // that is not 1024-aligned needs nothing else: the descriptor's base-offset field stays 0 (setting it to the
+              // start row's phase was measured to read the wrong chunks).
+              const uint64_t b_desc = b_desc0 + uint64_t(kw_ * 8);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                umma_bf16(d_tmem, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit(&a_empty[as]);
+              if (++as == L::kNA) { as = 0; aph ^= 1; }
             }
-            umma_commit(&a_empty[as]);
-            if (++as == L::kNA) { as = 0; aph ^= 1; }
           }
           umma_commit(&b_empty[bs]);
           if (++bs == L::kNB) { bs = 0; bph ^= 1; }
+        };
+        for (int gi = 0; gi < n_groups; ++gi) {
+          taps(3);
+          while (extra_pos == gi + 1) {
+            taps(1);
+            extra_pos = next_extra_pos(++e);
+          }
         }
         umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -1314,12 +1481,13 @@ conv_wreuse_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   }
 }
 
-template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false, int EPI_CT = -1>
+template <int BLOCK_N, int KIND, bool SWAP = false, bool TWO = false, int EPI_CT = -1, bool WR = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, cudaStream_t stream,
-                       const CUtensorMap* ta2_opt = nullptr) {
+                       const CUtensorMap* ta2_opt = nullptr, const CUtensorMap* tail_opt = nullptr) {
   const CUtensorMap& ta2 = ta2_opt ? *ta2_opt : ta;
+  const CUtensorMap& tail = tail_opt ? *tail_opt : ta;
   using L = SmemLayout<BLOCK_N, TWO>;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, KIND, SWAP, TWO, EPI_CT>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, KIND, SWAP, TWO, EPI_CT, WR>;
   GemmParams p = p_in;
   {
     // raster group: keep the group's B slice around 24 MB (L2 = 126 MB, shared with A tiles and the output stream)
@@ -1353,14 +1521,14 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ta2, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ta2, tail, p);
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
     return SVR2_OK;
   } else {
     int tiles = p.num_m_tiles * p.num_n_tiles;
     int grid = tiles < num_sms() ? tiles : num_sms();
     if (grid <= 0) return SVR2_OK;
-    kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, ta2, p);
+    kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, ta2, tail, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
     return SVR2_OK;
@@ -1655,7 +1823,16 @@ static int conv_wr_mode() {
   }
   return g_conv_wr;
 }
-extern "C" void svr2_set_conv_wreuse(int mode) { g_conv_wr = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+// the same switch for the CTA-pair kernels (Cout >= 256): SVR2_CONV_WR_PAIR, default = SVR2_CONV_WR's value
+static int g_conv_wr_pair = -1;
+static int conv_wr_pair_mode() {
+  if (g_conv_wr_pair < 0) {
+    const char* e = getenv("SVR2_CONV_WR_PAIR");
+    g_conv_wr_pair = e ? atoi(e) : conv_wr_mode();
+  }
+  return g_conv_wr_pair;
+}
+extern "C" void svr2_set_conv_wreuse(int mode) { g_conv_wr = g_conv_wr_pair = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 static void conv_tile_shape(int Cout, int H_out, int W_out, bool* swap_out, int* bw_out, int* bh_out) {
   const bool swap = (Cout > 64 && Cout <= 128) && (long long)H_out * W_out >= 256;
   int bw = 16, bh = 8;
@@ -1670,6 +1847,12 @@ static void conv_tile_shape(int Cout, int H_out, int W_out, bool* swap_out, int*
   } else {
     if (W_out >= 128 && H_out < 8) { bw = 128; bh = 1; }
     else if (W_out <= 8) { bw = 8; bh = 16; }
+    // CTA-pair W-reuse mainloop (Cout >= 256): m-tiles of one 128-pixel row segment, same waste rule
+    const int seg = (W_out + 127) / 128;
+    if (conv_wr_pair_mode() && Cout >= 256 && W_out >= 128 &&
+        (conv_wr_pair_mode() == 2 || (long long)seg * 128 * 100 <= (long long)W_out * 104)) {
+      bw = 128; bh = 1;
+    }
   }
   *swap_out = swap; *bw_out = bw; *bh_out = bh;
 }
@@ -1742,7 +1925,7 @@ static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, con
     long long bhn = (12LL << 20) / (row_bytes > 0 ? row_bytes : 1);
     if (bhn < 1) bhn = 1;
     if (bhn > (H_out + bh - 1) / bh) bhn = (H_out + bh - 1) / bh;
-    if (bw == 256 && bh == 1) {     // one-row tiles: 8 MB of input rows per frame (12 MB measured 1.6 x the DRAM reads)
+    if (bh == 1 && (bw == 256 || bw == 128) && kh == 3) {     // one-row tiles: 8 MB of input rows per frame (12 MB measured 1.6 x the DRAM reads)
       bhn = (8LL << 20) / (row_bytes > 0 ? row_bytes : 1);
       if (bhn < 2) bhn = 2;
       if (bhn > H_out) bhn = H_out;
@@ -1775,6 +1958,15 @@ static int conv3d_impl(const void* x, int T_in_total, int H, int W, int Cin, con
   if (swap && bw == 256 && bh == 1 && stride_hw == 1 && kh == 3 && kw == 3 && pad_hw == 1 && Cout <= 128 && Cout % 8 == 0)
     return launch_conv_wreuse(x, T_in_total, H, W, Cin, tb, p, (cudaStream_t)stream, x2 ? &ta2 : nullptr);
   if (swap) return launch_gemm<256, KIND_BF16, true>(ta, tb, p, (cudaStream_t)stream, x2 ? &ta2 : nullptr);
+  if (pair && bn == 256 && bw == 128 && bh == 1 && stride_hw == 1 && kh == 3 && kw == 3 && pad_hw == 1 && conv_wr_pair_mode()) {
+    CUtensorMap tail;            // 8-pixel boxes behind the 128-pixel row segment (the kw = 1, 2 taps' last pixels)
+    uint64_t d[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)T_in_total};
+    uint64_t s4[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t b_tail[4] = {BLOCK_K, 8, 1, 1};
+    rc = make_tmap_bf16(&tail, x, 4, d, s4, b_tail);
+    if (rc) return rc;
+    return launch_gemm<256, KIND_BF16, false, true, -1, true>(ta, tb, p, (cudaStream_t)stream, x2 ? &ta2 : nullptr, &tail);
+  }
   return dispatch_gemm(bn, ta, tb, p, (cudaStream_t)stream, pair, x2 ? &ta2 : nullptr);
 }
 
@@ -1788,16 +1980,24 @@ static int launch_conv_wreuse(const void* x, int T_in_total, int H, int W, int C
   if (rc) return rc;
   rc = make_tmap_bf16(&tail, x, 4, d, s, b_tail);
   if (rc) return rc;
+  // ring split (activation stages, weight stages): 3 + 5 (default) or 4 + 3 (SVR2_CONV_WR_RING=43, A/B)
+  static int ring = -1;
+  if (ring < 0) {
+    const char* e = getenv("SVR2_CONV_WR_RING");
+    ring = e ? atoi(e) : 35;
+  }
   static bool configured[kMaxDevices] = {};
   const int dev = current_device();
+  const int smem = ring == 43 ? WrSmem<4, 3>::kTotal : WrSmem<3, 5>::kTotal;
+  auto kern = ring == 43 ? conv_wreuse_kernel<4, 3> : conv_wreuse_kernel<3, 5>;
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wreuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WrSmem::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(SVR2_ERR_CUDA, cudaGetErrorString(e));
     configured[dev] = true;
   }
   const int grid = p.num_m_tiles < num_sms() ? p.num_m_tiles : num_sms();
   if (grid <= 0) return SVR2_OK;
-  conv_wreuse_kernel<<<grid, kNumThreads, WrSmem::kTotal, stream>>>(tx, tail, tw, tx2 ? *tx2 : tx, p);
+  kern<<<grid, kNumThreads, smem, stream>>>(tx, tail, tw, tx2 ? *tx2 : tx, p);
   return check_launch("conv_wreuse");
 }
 

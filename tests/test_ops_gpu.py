@@ -123,9 +123,13 @@ def _to_ndhwc(x_ncdhw, halo):
     (256, 128, (3, 3, 3), 1, 1, 2, 5, 520),      # W-reuse: three segments, ragged last one (8 valid pixels)
     (128, 96, (1, 3, 3), 1, 1, 2, 6, 512),       # W-reuse: kt = 1, Cout < 128
     (128, 128, (1, 3, 3), 1, 2, 2, 8, 1024),     # 256 x 1 tiles on the generic swap-AB kernel (stride 2: not eligible)
+    (256, 256, (3, 3, 3), 1, 1, 2, 6, 256),      # CTA-pair W-reuse mainloop: 128-pixel row segments, A descriptors shifted by kw rows
+    (256, 512, (3, 3, 3), 1, 1, 1, 3, 128),      # pair W-reuse: two n-tiles, odd number of m-tiles (phantom tile)
+    (512, 256, (1, 3, 3), 1, 1, 2, 5, 200),      # pair W-reuse: kt = 1, ragged second segment
+    (256, 256, (3, 3, 3), 2, 2, 3, 8, 512),      # 128 x 1 tiles on the generic pair kernel (stride 2: not eligible)
 ])
 def test_conv3d(svr2lib, Cin, Cout, k, st, shw, T, H, W):
-    if W >= 256:
+    if W >= 128:
         svr2lib.load().svr2_set_conv_wreuse(2)        # W-reuse tiles also where the last row segment is mostly empty
     x = rnd(1, Cin, T, H, W, seed=1)
     w = rnd(Cout, Cin, *k, std=(Cin * k[0] * k[1] * k[2]) ** -0.5, seed=2)
@@ -149,7 +153,7 @@ def test_conv3d(svr2lib, Cin, Cout, k, st, shw, T, H, W):
     svr2lib.load().svr2_set_conv_wreuse(1)
     assert_close(y[2:], ref_nd, 4e-3, "conv3d body")
     assert torch.equal(y[0], y[2]) and torch.equal(y[1], y[2]), "halo frames must replicate frame 0"
-    if W >= 256 and shw == 1 and k[1] == 3:           # the generic swap-AB kernel on the same problem: same products,
+    if W >= 128 and shw == 1 and k[1] == 3:           # the generic kernel on the same problem: same products,
         y0 = torch.zeros_like(y)                      # another summation order of the fp32 accumulation
         svr2lib.load().svr2_set_conv_wreuse(0)
         try:
@@ -166,6 +170,7 @@ def test_conv3d(svr2lib, Cin, Cout, k, st, shw, T, H, W):
     (256, 128, 256, 2, 17, 33),     # encoder down1.res0 (odd sizes)
     (512, 256, 512, 1, 9, 16),      # encoder down2.res0, single frame
     (128, 256, 128, 2, 7, 512),     # W-reuse kernel with the shortcut's extra k-blocks
+    (256, 512, 256, 2, 5, 256),     # CTA-pair W-reuse mainloop with the shortcut's extra k-blocks
 ])
 def test_conv3d_fused_shortcut(svr2lib, Cin, C2, Cout, T, H, W):
     """conv2(h) + conv_shortcut(x) as one contraction over [h ; x] (ResnetBlock3D, attn_video_vae.py:311-362) vs torch:

@@ -34,6 +34,25 @@ for s in $STAGES; do
     ab_attn2) for v in 0 1; do echo "--- SVR2_ATTN_PTMEM=$v"; SVR2_ATTN_PTMEM=$v timeout 300 python -m pytest tests/test_ops_gpu.py tests/test_models_gpu.py -q -k "attn or attention or dit_vs_golden" 2>&1 | tail -3
                 for i in 1 2 3; do SVR2_ATTN_PTMEM=$v PERF_REPS=20 python tools/perf_conv_one.py attn 2>&1 | tail -1; done
               done 2>&1 | tee gpurun_out/r2_ab_attn2.log ;;
+    ab_wr3)   for cfg in "SVR2_CONV_WR_RING=35" "SVR2_CONV_WR_RING=43"; do echo "--- $cfg"
+                for c in conv128 conv_sc; do for i in 1 2; do env $cfg PERF_REPS=10 python tools/perf_conv_one.py $c 2>&1 | tail -1; done; done
+              done 2>&1 | tee gpurun_out/r2_ab_wr3.log
+              SVR2_CONV_WR_RING=43 timeout 200 python -m pytest tests/test_ops_gpu.py -q -x -k "conv3d" 2>&1 | tail -2 ;;
+    ab_wrp)   timeout 300 python -m pytest tests/test_ops_gpu.py -q -x -k "conv3d" 2>&1 | tail -4
+              for cfg in "SVR2_CONV_WR_PAIR=0" "SVR2_CONV_WR_PAIR=1"; do echo "--- $cfg"
+                for i in 1 2 3; do env $cfg PERF_REPS=10 python tools/perf_conv_one.py conv256 2>&1 | tail -1; done
+              done 2>&1 | tee gpurun_out/r2_ab_wrp.log
+              timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -c 1 -f -o gpurun_out/r2_conv256_wr python tools/perf_conv_one.py conv256 > gpurun_out/r2_ncu_conv256_wr.log 2>&1; tail -2 gpurun_out/r2_ncu_conv256_wr.log ;;
+    ab_noshift) for cfg in "SVR2_WR_NOSHIFT=0" "SVR2_WR_NOSHIFT=1"; do echo "--- $cfg"
+                for c in conv256 conv128; do env $cfg PERF_REPS=10 python tools/perf_conv_one.py $c 2>&1 | tail -1; done
+                env $cfg timeout 300 ncu --metrics sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.avg.per_second,gpu__time_duration.sum,l1tex__data_bank_conflicts_pipe_lsu.sum,smsp__inst_executed.sum --clock-control none -k regex:"gemm_tcgen05|conv_wreuse" -c 1 python tools/perf_conv_one.py conv256 2>&1 | grep -E "tensor_cycles|per_second|duration" 
+                env $cfg timeout 300 ncu --metrics sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.avg.per_second,gpu__time_duration.sum --clock-control none -k regex:"gemm_tcgen05|conv_wreuse" -c 1 python tools/perf_conv_one.py conv128 2>&1 | grep -E "tensor_cycles|per_second|duration"
+              done 2>&1 | tee gpurun_out/r2_ab_noshift.log ;;
+    ab_wr4)   timeout 300 python -m pytest tests/test_ops_gpu.py -q -x -k "conv3d" 2>&1 | tail -2
+              for cfg in "SVR2_CONV_WR=0" "SVR2_CONV_WR=1"; do echo "--- $cfg"
+                for c in conv256 conv128 conv_sc; do for i in 1 2; do env $cfg PERF_REPS=10 python tools/perf_conv_one.py $c 2>&1 | tail -1; done; done
+                for c in conv256 conv128; do env $cfg timeout 300 ncu --metrics sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.avg.per_second,gpu__time_duration.sum --clock-control none -k regex:"gemm_tcgen05|conv_wreuse" -c 1 python tools/perf_conv_one.py $c 2>&1 | grep -E "tensor_cycles|per_second|duration"; done
+              done 2>&1 | tee gpurun_out/r2_ab_wr4.log ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2_launches.csv python bench.py --workload 1080p --steps 1 --warmup 1 --no_graph --lib-baseline none --no-cpu-baseline > gpurun_out/r2_launches_bench.log 2>&1; tail -2 gpurun_out/r2_launches_bench.log | cut -c1-300 ;;
     ncu_conv) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -c 1 -f -o gpurun_out/r2_conv256 python tools/perf_conv_one.py conv256 > gpurun_out/r2_ncu_conv256.log 2>&1; tail -2 gpurun_out/r2_ncu_conv256.log ;;
     debug_native) timeout 300 python tools/debug_native.py > gpurun_out/r2_debug_native.log 2>&1; cat gpurun_out/r2_debug_native.log | tail -14 ;;
