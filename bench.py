@@ -300,6 +300,7 @@ def main():
     # ---- region P: the same steps with per-kernel CUDA events on the launching stream (per-call events need the Python
     # sequencing of the same kernels): the roofline and the per-kernel table come from here, not the headline value
     prof_steps = 1 if ms / args.steps > 5000 else min(args.steps, 3)      # long clips: one profiled pass is enough
+    lib.release_workspace(dev)      # the call-by-call sequencing allocates per activation: it needs the resident block's bytes
     step(frames_dev)            # the Python sequencing allocates per activation: first pass fills the allocator's cache
     lib.PROFILER = lib.Profiler()
     lib.PROFILER.detail = args.detail
@@ -451,6 +452,7 @@ def main():
         "clocks": sampler.result(),
     }
     if args.lib_baseline != "none" and not vae_only:
+        lib.release_workspace(dev)       # the library flow allocates through torch: give it the engine's resident block
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import gpu_library_baseline as glb

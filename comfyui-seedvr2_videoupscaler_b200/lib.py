@@ -270,6 +270,58 @@ def conv3d(x, T_in_total, H, W, Cin, w, Cout, k, stride_t, stride_hw, pad_hw, T_
 
 
 # --------------------------------------------------------------------------
+# engine workspace: ONE resident block per device for the native runtimes (a clip's encode / DiT / decode phases share it)
+# --------------------------------------------------------------------------
+_WORKSPACES = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """uint8 CUDA tensor of >= nbytes.  Outside a CUDA-graph capture the block is kept resident and reused (grown when
+    a larger clip arrives): handing ~100 GB back to the caching allocator after every clip lets other allocations land
+    inside the freed segment, and the next clip's request then neither fits the fragments nor a fresh cudaMalloc.
+    Inside a capture the block comes from the graph's private pool.  One stream at a time uses the block."""
+    device = torch.device(device)
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, device=device, dtype=torch.uint8)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    t = _WORKSPACES.get(key)
+    if t is None or t.numel() < nbytes:
+        if t is not None:
+            del t
+            release_workspace(device)
+        try:
+            t = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        except torch.OutOfMemoryError:
+            torch.cuda.synchronize(device)
+            torch.cuda.empty_cache()
+            t = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        _WORKSPACES[key] = t
+    return t
+
+
+def workspace_held(device) -> int:
+    device = torch.device(device)
+    t = _WORKSPACES.get(device.index if device.index is not None else torch.cuda.current_device())
+    return 0 if t is None else t.numel()
+
+
+def release_workspace(device=None) -> None:
+    """Drop the resident block(s) — before a CUDA-graph capture of a clip (its pool holds its own) or when another
+    consumer needs the HBM."""
+    if device is None:
+        had = bool(_WORKSPACES)
+        _WORKSPACES.clear()
+    else:
+        device = torch.device(device)
+        had = _WORKSPACES.pop(device.index if device.index is not None else torch.cuda.current_device(), None) is not None
+    # back to the DRIVER, not to the caching allocator: a cached ~100 GB segment gets split by whatever is allocated next,
+    # and one small long-lived tensor inside it keeps the whole segment from ever being handed out again in one piece
+    if had and not torch.cuda.is_current_stream_capturing():
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
+
+# --------------------------------------------------------------------------
 # handle API (native host runtime, csrc/engine.cu)
 # --------------------------------------------------------------------------
 _TORCH_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}

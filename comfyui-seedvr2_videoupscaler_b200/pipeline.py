@@ -88,8 +88,8 @@ class SeedVR2Engine:
         """ONE workspace for the three phases of a clip of T (4n+1) frames at Hp x Wp (multiples of 16): the maximum of
         the exact needs of VAE encode, the DiT forward and VAE decode (svr2_vae_workspace_bytes / svr2_workspace_bytes),
         with the VAE passes temporally sliced until they fit the free HBM.  The phases run one after the other on one
-        stream, so they can share the bytes; the block comes from torch's caching allocator (the capture pool inside a
-        CUDA graph) and goes back to it after the clip.  None when a phase runs on the Python sequencing (profiling)."""
+        stream, so they can share the bytes; the block is the engine's resident workspace (lib.workspace: kept between clips,
+        grown on demand; the capture pool inside a CUDA graph).  None when a phase runs on the Python sequencing (profiling)."""
         from . import lib
         if not (self.vae._use_native() and self.dit.native and lib.PROFILER is None):
             return None
@@ -97,7 +97,7 @@ class SeedVR2Engine:
         budget = int(0.92 * self.vae._free_bytes()) - 2 * 3 * T * Hp * Wp * 2      # the decoded clip and its crop
         need = max(self.vae.plan_slices(True, T, Hp, Wp, budget)[1], self.vae.plan_slices(False, Tl, h, w, budget)[1],
                    self.dit.workspace_bytes(Tl, h, w, self.txt.shape[0]))
-        return torch.empty(need, device=self.device, dtype=torch.uint8)
+        return lib.workspace(need, self.device)
 
     def latent_shape(self, frames: torch.Tensor, resolution: Optional[int] = None, max_resolution: int = 0):
         """(T', h, w, 16) of the latent ``upscale_clip`` will produce for ``frames`` (T,h,w,3)."""
@@ -251,9 +251,10 @@ class GraphedClip:
                 for _ in range(warmup):
                     engine.upscale_clip(self.static_in, noise=self.noise, **clip_kwargs)
             torch.cuda.current_stream(dev).wait_stream(side)
-        # the graph's private pool holds one whole clip of intermediates (~100 GB at 4K): hand the eager path's cached
-        # blocks back first so both never have to coexist
+        # the graph's private pool holds one whole clip of intermediates (~100 GB at 4K): hand the eager path's resident
+        # workspace and cached blocks back first so both never have to coexist
         torch.cuda.synchronize(dev)
+        lib.release_workspace(dev)
         torch.cuda.empty_cache()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

@@ -138,8 +138,10 @@ class B200VideoVAE(EngineModule):
         return self.native and lib.PROFILER is None and self.fuse_shortcut and self.single_pass_attention
 
     def _free_bytes(self) -> int:
+        """Free HBM incl. torch's cached blocks and the engine's resident workspace (it is regrown on demand)."""
         free, _ = torch.cuda.mem_get_info(self.device)
-        return free + torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        held = 0 if torch.cuda.is_current_stream_capturing() else lib.workspace_held(self.device)
+        return free + torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device) + held
 
     def plan_slices(self, encode: bool, T: int, H: int, W: int, budget: Optional[int] = None):
         """(slice_frames, workspace bytes) of a native encode (T sample frames of H x W) / decode (T latent frames of
@@ -162,8 +164,8 @@ class B200VideoVAE(EngineModule):
         return sz, need
 
     def _native_run(self, encode: bool, src: torch.Tensor, T: int, H: int, W: int, out: torch.Tensor, workspace=None):
-        """``workspace``: a uint8 CUDA tensor shared by the phases of a clip (pipeline.ClipWorkspace) or None — then it
-        comes from torch's caching allocator (the capture pool inside a CUDA graph) and returns to it after the call."""
+        """``workspace``: a uint8 CUDA tensor shared by the phases of a clip (pipeline.SeedVR2Engine.clip_workspace) or None —
+        then the engine's resident block (lib.workspace; the capture pool inside a CUDA graph)."""
         if workspace is not None:
             sz, need = self.plan_slices(encode, T, H, W, budget=workspace.numel())
             if need > workspace.numel():
@@ -171,7 +173,7 @@ class B200VideoVAE(EngineModule):
             ws = workspace
         else:
             sz, need = self.plan_slices(encode, T, H, W)
-            ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+            ws = lib.workspace(need, self.device)
         dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[src.dtype]
         lib.call("svr2_vae_encode" if encode else "svr2_vae_decode", self.native_handle(), lib.ptr(src), dt, T, H, W, sz,
                  lib.ptr(out), lib.ptr(ws), ws.numel(), lib.stream())

@@ -39,3 +39,15 @@ def pkg():
 def svr2lib(pkg):
     import importlib
     return importlib.import_module("comfyui_seedvr2_videoupscaler_b200.lib")
+
+
+@pytest.fixture(autouse=True)
+def _release_engine_workspace():
+    """The native runtimes keep one resident workspace per device (lib.workspace); tests that run the torch oracle on the
+    same GPU right after need those bytes."""
+    yield
+    lib = sys.modules.get("comfyui_seedvr2_videoupscaler_b200.lib")
+    if lib is not None:
+        import torch
+        if torch.cuda.is_available():
+            lib.release_workspace()

@@ -53,6 +53,7 @@ for s in $STAGES; do
                 for c in conv256 conv128 conv_sc; do for i in 1 2; do env $cfg PERF_REPS=10 python tools/perf_conv_one.py $c 2>&1 | tail -1; done; done
                 for c in conv256 conv128; do env $cfg timeout 300 ncu --metrics sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.avg.per_second,gpu__time_duration.sum --clock-control none -k regex:"gemm_tcgen05|conv_wreuse" -c 1 python tools/perf_conv_one.py $c 2>&1 | grep -E "tensor_cycles|per_second|duration"; done
               done 2>&1 | tee gpurun_out/r2_ab_wr4.log ;;
+    ab_bench) for v in 0 1; do SVR2_CONV_WR_PAIR=$v timeout 600 python bench.py --steps 3 --warmup 2 --lib-baseline none --no-cpu-baseline --no_graph --phases > gpurun_out/r2_ab_bench_pair$v.json 2> gpurun_out/r2_ab_bench_pair$v.txt; cut -c1-200 gpurun_out/r2_ab_bench_pair$v.json; echo; done ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r2_launches.csv python bench.py --workload 1080p --steps 1 --warmup 1 --no_graph --lib-baseline none --no-cpu-baseline > gpurun_out/r2_launches_bench.log 2>&1; tail -2 gpurun_out/r2_launches_bench.log | cut -c1-300 ;;
     ncu_conv) timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -c 1 -f -o gpurun_out/r2_conv256 python tools/perf_conv_one.py conv256 > gpurun_out/r2_ncu_conv256.log 2>&1; tail -2 gpurun_out/r2_ncu_conv256.log ;;
     debug_native) timeout 300 python tools/debug_native.py > gpurun_out/r2_debug_native.log 2>&1; cat gpurun_out/r2_debug_native.log | tail -14 ;;
