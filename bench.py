@@ -301,9 +301,9 @@ def main():
     # sequencing of the same kernels): the roofline and the per-kernel table come from here, not the headline value
     prof_steps = 1 if ms / args.steps > 5000 else min(args.steps, 3)      # long clips: one profiled pass is enough
     lib.release_workspace(dev)      # the call-by-call sequencing allocates per activation: it needs the resident block's bytes
-    step(frames_dev)            # the Python sequencing allocates per activation: first pass fills the allocator's cache
-    lib.PROFILER = lib.Profiler()
+    lib.PROFILER = lib.Profiler()   # (set BEFORE the warm pass: with no profiler the step would run natively and re-create the block)
     lib.PROFILER.detail = args.detail
+    step(frames_dev)            # the Python sequencing allocates per activation: first pass fills the allocator's cache
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     lib.PROFILER.reset()
