@@ -46,9 +46,10 @@ const char* svr2_last_error(void);
 /* 1: GEMM/conv tiles are executed by CTA pairs (tcgen05 cta_group::2, 256-row tiles); 0: single-CTA tiles.
  * Default from the environment variable SVR2_CTA_PAIR (unset = library default). */
 void svr2_set_cta_pair(int on);
-/* Cout <= 128 stride-1 3x3 convs: 0 = generic swap-AB tiles (32 x 8 pixels), 1 (default) = the W-reuse kernel (tiles of one
- * 256-pixel row segment, the three horizontal taps read one activation stage) where rows split into segments with <= 4 %
- * waste, 2 = wherever a row holds a segment.  Default from SVR2_CONV_WR.  Changes svr2_conv_stat_slots(). */
+/* Stride-1 3x3 convs: 0 = generic tiles (32 x 8 / 16 x 8 pixels), 1 (default) = the W-reuse kernel for Cout <= 128 (tiles of
+ * one 256-pixel row segment, the three horizontal taps read one activation stage) where rows split into segments with <= 4 %
+ * waste, 2 = wherever a row holds a segment and also in the CTA-pair kernels (Cout >= 256, 128-pixel segments), 3 = 1 + the
+ * CTA-pair kernels under the waste rule.  Default from SVR2_CONV_WR.  Changes svr2_conv_stat_slots(). */
 void svr2_set_conv_wreuse(int mode);
 int svr2_version(void);
 /* fills sm count / major / minor of the current device; SVR2_ERR_ARCH unless sm_100 */
