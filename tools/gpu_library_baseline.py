@@ -165,8 +165,7 @@ def phase_level(workload="cfg2", engine=None, dev="cuda", variant="3b"):
     x0 = engine.inference(noise, lat)
     res["engine_ms"] = {"encode": ev(lambda: engine.vae_encode(x)), "dit": ev(lambda: engine.inference(noise, lat)),
                         "decode": ev(lambda: engine.vae_decode(x0))}
-    import importlib
-    importlib.import_module("comfyui_seedvr2_videoupscaler_b200.lib").release_workspace()   # the library flow needs the engine's resident block
+    sys.modules["comfyui_seedvr2_videoupscaler_b200.lib"].release_workspace()   # the library flow needs the engine's resident block
     torch.cuda.empty_cache()
     # ---- library flow (same synthetic weights, regenerated from the seeds build_synthetic_engine uses)
     vae_sd = pkg.weights.synth_vae_state_dict(seed=1235, dtype=torch.float16, device=dev)
