@@ -349,6 +349,9 @@ def main():
     if graphed is not None:                   # one untimed replay: first-replay graph upload is not steady state
         graphed(frames_host.to(dev, non_blocking=True))
         torch.cuda.synchronize()
+    else:                                     # eager: one untimed step re-creates the engine's resident workspace (released for
+        step(frames_host.to(dev, non_blocking=True))      # the profiled region) outside the timed region
+        torch.cuda.synchronize()
     e2.record()
     for _ in range(args.steps):
         src = frames_host.to(dev, non_blocking=True)
