@@ -309,15 +309,18 @@ def release_workspace(device=None) -> None:
     """Drop the resident block(s) — before a CUDA-graph capture of a clip (its pool holds its own) or when another
     consumer needs the HBM."""
     if device is None:
-        had = bool(_WORKSPACES)
+        keys = list(_WORKSPACES)
         _WORKSPACES.clear()
     else:
         device = torch.device(device)
-        had = _WORKSPACES.pop(device.index if device.index is not None else torch.cuda.current_device(), None) is not None
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        keys = [key] if _WORKSPACES.pop(key, None) is not None else []
+    had = bool(keys)
     # back to the DRIVER, not to the caching allocator: a cached ~100 GB segment gets split by whatever is allocated next,
     # and one small long-lived tensor inside it keeps the whole segment from ever being handed out again in one piece
     if had and not torch.cuda.is_current_stream_capturing():
-        torch.cuda.synchronize()
+        for k in keys:
+            torch.cuda.synchronize(k)
         torch.cuda.empty_cache()
 
 

@@ -347,6 +347,25 @@ def test_vae_native_runtime_equals_python_sequencing(vae_pair, split):
     assert torch.equal(out, ref)
 
 
+def test_engine_workspace_is_resident_and_goes_back_to_the_driver(pkg):
+    """lib.workspace: one resident block per device (reused for smaller requests, regrown for larger ones), released to
+    the driver — not to the caching allocator — by release_workspace()."""
+    lib = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.lib")
+    lib.release_workspace()
+    a = lib.workspace(1 << 20, "cuda")
+    assert a.is_cuda and a.dtype == torch.uint8 and a.numel() >= 1 << 20 and lib.workspace_held("cuda") == a.numel()
+    ptr = a.data_ptr()
+    b = lib.workspace(1 << 19, "cuda")
+    assert b.data_ptr() == ptr
+    del a, b
+    c = lib.workspace(1 << 22, "cuda")
+    assert c.numel() >= 1 << 22 and lib.workspace_held("cuda") == c.numel()
+    del c
+    reserved = torch.cuda.memory_reserved()
+    lib.release_workspace("cuda")
+    assert lib.workspace_held("cuda") == 0 and torch.cuda.memory_reserved() <= reserved
+
+
 def test_vae_attention_single_pass_equals_two_pass_and_falls_back(vae_pair):
     """Mid-block attention (attn_video_vae.py:656-668): the single-pass path (sampled reference exponent, un-normalised
     probabilities, row-sum division in the P V epilogue) against the exact two-pass path on the same input, and the
