@@ -6,13 +6,14 @@
 //      O_i = softmax(Q_i K_i^T / sqrt(128)) V_i        (non-causal, no mask)
 // on the packed (total, heads, 128) bf16 layout with int32 cu_seqlens.
 //
-// One CTA per (q-tile of 128 rows, sequence, head); 6 warps:
-//   warp 0    : TMA producer  (Q once, then a 2-stage ring of K/V tiles, 128B swizzle)
-//   warp 1    : MMA issuer    (S = Q K^T and O += P V, tcgen05.mma M=128,N=128,K=16, fp32 in TMEM;
-//                              V is consumed straight from its row-major tile as an MN-major B operand)
-//   warps 2-5 : softmax       (one query row per thread: tcgen05.ld the S row, online softmax in
-//                              registers with exp2, P -> bf16 -> swizzled smem as the A operand of P·V,
-//                              lazy rescale of O in TMEM, final 1/l and store)
+// Persistent CTAs (two per SM) walk the work list (q-tile of 128 rows, head, sequence); 6 warps:
+//   warp 0    : TMA producer  (Q per item, a 2-stage ring of K tiles and a V tile, 128B swizzle; runs ahead into the next item)
+//   warp 1    : MMA issuer    (S = Q K^T: SS-MMA M=128,N=64,K=16; O += P V: TS-MMA with P as the A operand in tensor
+//                              memory, V consumed straight from its row-major tile as an MN-major B operand; fp32 in TMEM)
+//   warps 2-5 : softmax       (one query row per thread: tcgen05.ld the S row, online softmax in registers with exp2
+//                              and a thresholded rescale, P -> bf16 pairs -> tcgen05.st into 32 TMEM columns,
+//                              final 1/l and the scatter store through out_row_map)
+// (PTM = false keeps the earlier path: P through swizzled shared memory + fence.proxy.async, an SS-MMA for P V.)
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>

@@ -133,7 +133,67 @@ int conv_tap_gather_strided(const float* z, int64_t ldz, int co_n, const void* b
 }
 }  // namespace svr2
 
+// Arena fuzz: a random alloc / release / alloc_top sequence replayed on an unbounded arena (the dry run) and on one capped
+// at the dry run's need() must make identical placement decisions, never overlap two live blocks and stay inside the cap.
+static int arena_fuzz(unsigned seed, int ops) {
+  struct Blk { size_t off, bytes; };
+  auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return seed >> 8; };
+  std::vector<int> script;           // >0: alloc of that many bytes; 0: release a pseudo-random live block; <0: alloc_top
+  std::vector<size_t> pick;
+  for (int i = 0; i < ops; ++i) {
+    const unsigned r = rnd() % 100;
+    if (r < 55) script.push_back(1 + (int)(rnd() % (1 << (4 + rnd() % 18))));
+    else if (r < 95) script.push_back(0);
+    else script.push_back(-(1 + (int)(rnd() % 100000)));
+    pick.push_back(rnd());
+  }
+  auto replay = [&](Arena& A, std::vector<size_t>* trace) -> bool {
+    std::vector<Blk> live, top;
+    for (size_t i = 0; i < script.size(); ++i) {
+      const int op = script[i];
+      if (op > 0) {
+        const size_t off = A.alloc((size_t)op);
+        if (off == NONE) return false;
+        const size_t bytes = align_up((size_t)op);
+        for (const Blk& b : live)
+          if (off < b.off + b.bytes && b.off < off + bytes) return false;          // overlap with a live block
+        if (off + bytes > A.cap - A.top_used) return false;
+        live.push_back({off, bytes});
+        trace->push_back(off);
+      } else if (op == 0) {
+        if (live.empty()) continue;
+        const size_t k = pick[i] % live.size();
+        A.release(live[k].off, live[k].bytes);
+        live.erase(live.begin() + k);
+      } else {
+        const size_t off = A.alloc_top((size_t)(-op));
+        if (off == NONE) return false;
+        trace->push_back(A.top_used);
+        for (const Blk& b : live)
+          if (b.off + b.bytes > A.cap - A.top_used) return false;                   // the top region ran into a live block
+      }
+    }
+    return true;
+  };
+  Arena dry(~(size_t)0 / 2);
+  std::vector<size_t> t0, t1;
+  if (!replay(dry, &t0)) return 1;
+  Arena real(dry.need());
+  if (!replay(real, &t1)) return 2;
+  if (t0 != t1) return 3;
+  if (real.need() != dry.need()) return 4;
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 2 && std::string(argv[1]) == "fuzz") {
+    for (unsigned seed = 1; seed <= 200; ++seed) {
+      const int rc = arena_fuzz(seed, 400);
+      if (rc) { fprintf(stderr, "arena fuzz seed %u failed (%d)\n", seed, rc); return 10 + rc; }
+    }
+    printf("arena fuzz ok\n");
+    return 0;
+  }
   if (argc < 7) return 2;
   svr2_engine eng;
   eng.desc.variant = 2;

@@ -136,3 +136,10 @@ def test_native_vae_plan_shrinks_with_slices(cpu_vae, tracer, tmp_path):
     assert s1 < s2 < full
     full, s8, s4 = need("enc", 33, 272, 480, 0), need("enc", 33, 272, 480, 8), need("enc", 33, 272, 480, 4)
     assert s4 < s8 < full
+
+
+def test_native_vae_arena_fuzz(tracer):
+    """The activation arena: 200 random alloc / release / top-allocation scripts replayed on the unbounded (dry-run) arena
+    and on one capped at the dry run's size — identical placements, no overlap of live blocks, nothing beyond the cap."""
+    r = subprocess.run([tracer, "fuzz"], capture_output=True, text=True)
+    assert r.returncode == 0 and "arena fuzz ok" in r.stdout, (r.returncode, r.stderr[-500:])
