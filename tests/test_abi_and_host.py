@@ -310,3 +310,30 @@ def test_clip_runner_control_flow_with_stubbed_kernels(pkg, monkeypatch):
     vid = eng.upscale_video(torch.rand(13, 20, 30, 3), batch_size=5, temporal_overlap=2, resolution=40)
     assert vid.shape == (13, 40, 60, 3)
     assert tuple(eng.latent_shape(frames, 40)) == (3, 6, 8, 16)
+
+
+def test_vae_slice_search_picks_the_longest_slice_that_fits(pkg, monkeypatch):
+    """B200VideoVAE.plan_slices: un-sliced first, then set_causal_slicing's split, then shorter slices — the first whose
+    exact workspace (stubbed here: the native dry run needs no GPU but the module's constructor does) fits the budget."""
+    vae = importlib.import_module("comfyui_seedvr2_videoupscaler_b200.vae")
+    eng = object.__new__(vae.B200VideoVAE)
+    eng.split_size = None
+    asked = []
+
+    def fake_ws(encode, T, H, W, sl=0):
+        asked.append(sl)
+        frames = (T if sl == 0 else min(T, sl + 1))
+        return 100 * frames + (50 if sl else 0)            # bytes grow with the slice length; slicing state costs 50
+
+    monkeypatch.setattr(eng, "workspace_bytes", fake_ws, raising=False)
+    assert eng.plan_slices(False, 17, 8, 8, budget=10 ** 6) == (0, 1700) and asked == [0]
+    del asked[:]
+    sz, need = eng.plan_slices(False, 17, 8, 8, budget=1000)            # 100 * (sz + 1) + 50 <= 1000 -> sz = 8
+    assert (sz, need) == (8, 950) and asked[0] == 0 and asked[1:] == list(range(15, 7, -1))      # shrinks one frame at a time
+    sz, need = eng.plan_slices(True, 33, 64, 64, budget=1400)           # encode: multiples of 4: 100 * 13 + 50 = 1350
+    assert (sz, need) == (12, 1350)
+    assert eng.plan_slices(True, 10, 64, 64, budget=10)[0] == 0         # not 4n+1 frames: never sliced
+    eng.split_size = 16                                                 # set_causal_slicing(split_size=16 sample frames)
+    assert eng.plan_slices(False, 17, 8, 8, budget=10 ** 6) == (4, 550)
+    assert eng.plan_slices(True, 33, 64, 64, budget=10 ** 6) == (16, 1750)
+    assert eng.plan_slices(False, 4, 8, 8, budget=10 ** 6) == (0, 400)  # the clip is shorter than the split
